@@ -1,0 +1,81 @@
+"""Forward dispatch of ``models.MobileNetSkipAdd`` onto the C-ABI (one ``fd_forward`` per call).
+
+Replaces the Python layer loop of reference models.py:706-732 and every PyTorch operator it
+launches.  The engine is created lazily on the first forward so that
+modules restored by ``torch.load`` without ``__init__`` (reference main.py:49-57) work.
+"""
+import torch
+
+from . import plan as _plan
+
+_SUPPORTED = (torch.float32, torch.float16, torch.bfloat16)
+
+
+class SkipAddEngine:
+    def __init__(self, module):
+        self.module = module
+        self.plans = {}          # (device index, n, h, w, dtype) -> Plan
+        self.signature = None
+        self.options = {}
+
+    # -- weight freshness ----------------------------------------------------------------------
+    def _weights_signature(self):
+        """Cheap per-call check that catches .cuda()/.half()/.to()/load_state_dict().
+        In-place edits of a single layer need an explicit ``refresh()``."""
+        w0 = self.module.conv0[0].weight
+        bn = self.module.decode_conv6[1]
+        return (w0.data_ptr(), w0.dtype, w0._version, bn.running_var.data_ptr(), bn.running_var._version,
+                bn.weight._version)
+
+    def refresh(self):
+        """Drop packed weights (call after editing parameters in place)."""
+        for p in self.plans.values():
+            p.close()
+        self.plans.clear()
+        self.signature = None
+
+    def set_option(self, name, value):
+        """Forwarded to ``fd_plan_set_option`` on every current and future plan."""
+        self.options[name] = int(value)
+        for p in self.plans.values():
+            p.set_option(name, value)
+
+    # -- forward ---------------------------------------------------------------------------------
+    def plan_for(self, x):
+        m = self.module
+        if m.training:
+            raise RuntimeError("fastdepth_b200 is inference-only: call model.eval() first "
+                               "(BatchNorm is folded from running statistics, reference main.py:65)")
+        if not x.is_cuda:
+            raise RuntimeError("fastdepth_b200: MobileNetSkipAdd.forward needs a CUDA tensor; "
+                               "there is no CPU fallback (use models.MobileNet for CPU plumbing)")
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise RuntimeError("expected input [N,3,H,W], got %s" % (tuple(x.shape),))
+        wdtype = m.conv0[0].weight.dtype
+        if x.dtype != wdtype:
+            raise RuntimeError("Input type (%s) and weight type (%s) should be the same" % (x.dtype, wdtype))
+        if x.dtype not in _SUPPORTED:
+            raise RuntimeError("unsupported dtype %s" % x.dtype)
+        n, _, h, w = x.shape
+        if h % 32 or w % 32:
+            raise RuntimeError("The size of tensor a must match the size of tensor b: H and W must be multiples "
+                               "of 32 for the skip connections to line up, got %dx%d" % (h, w))
+        sig = self._weights_signature()
+        if sig != self.signature:
+            self.refresh()
+            self.signature = sig
+        key = (x.device.index, n, h, w, x.dtype)
+        p = self.plans.get(key)
+        if p is None:
+            p = _plan.Plan.from_module(m, n, h, w, x.dtype, x.device.index)
+            for k, v in self.options.items():
+                p.set_option(k, v)
+            self.plans[key] = p
+        return p
+
+    def __call__(self, x):
+        p = self.plan_for(x)
+        xc = x if x.is_contiguous() else x.contiguous()
+        y = torch.empty((x.shape[0], 1, x.shape[2], x.shape[3]), dtype=x.dtype, device=x.device)
+        p.forward(xc, y, torch.cuda.current_stream(x.device).cuda_stream)
+        return y

@@ -1,0 +1,231 @@
+"""Host-side planning: read a MobileNetSkipAdd-shaped module, fold BatchNorm, describe the
+stages and hand everything to the C-ABI.
+
+The module is only *read* here (conv weights, BN statistics, strides): attribute access is
+limited to ``.weight/.stride/.kernel_size/.groups`` of convs and
+``.weight/.bias/.running_mean/.running_var/.eps`` of BNs so that modules unpickled from old
+PyTorch versions (missing newer attributes) still work (checkpoint row).
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import StageDesc
+
+DTYPE_CODE = {torch.float32: _lib.FD_F32, torch.float16: _lib.FD_F16, torch.bfloat16: _lib.FD_BF16}
+N_METRICS = 11
+METRIC_NAMES = ('irmse', 'imae', 'mse', 'rmse', 'mae', 'absrel', 'lg10', 'delta1', 'delta2', 'delta3')
+
+# encoder block i -> skip consumer: decode stage j adds the output of encoder block SKIP[j]
+# (reference models.py:714-719, 724-729)
+SKIP_FOR_DECODE = {2: 5, 3: 3, 4: 1}
+
+
+def fold_bn(bn):
+    """Eval-mode BatchNorm2d as y = x*scale + bias, folded in fp32 (exact to ~4e-6 rel).
+    reference: nn.BatchNorm2d in conv_bn/conv_dw/depthwise/pointwise, eps 1e-5."""
+    g = bn.weight.detach().float().cpu()
+    b = bn.bias.detach().float().cpu()
+    m = bn.running_mean.detach().float().cpu()
+    v = bn.running_var.detach().float().cpu()
+    scale = g / torch.sqrt(v + float(bn.eps))
+    bias = b - m * scale
+    return scale.contiguous().numpy(), bias.contiguous().numpy()
+
+
+def _act_of(m):
+    if isinstance(m, nn.ReLU6):
+        return _lib.FD_ACT_RELU6
+    if isinstance(m, nn.ReLU):
+        return _lib.FD_ACT_RELU
+    raise RuntimeError('unsupported activation %r on the hot path' % type(m).__name__)
+
+
+def _w(conv):
+    return np.ascontiguousarray(conv.weight.detach().float().cpu().numpy())
+
+
+def _sq(v):
+    return int(v[0]) if isinstance(v, (tuple, list)) else int(v)
+
+
+def describe(module):
+    """Walk conv0..conv13, decode_conv1..6 and return (stage descs, per-stage weight tuples).
+
+    Mirrors the dispatch of reference models.py:706-732: 14 encoder blocks with skips saved
+    after blocks 1/3/5, five decoder blocks each followed by nearest x2 (+skip for 2/3/4), head."""
+    descs, weights, names = [], [], []
+    conv0 = module.conv0
+    c, bn, act = conv0[0], conv0[1], conv0[2]
+    descs.append(dict(kind=_lib.FD_STAGE_STEM, c_in=c.weight.shape[1], c_out=c.weight.shape[0],
+                      ksize=_sq(c.kernel_size), stride=_sq(c.stride), act=_act_of(act), upsample=0, skip_src=-1))
+    s, b = fold_bn(bn)
+    weights.append((None, None, None, _w(c), s, b))
+    names.append('conv0')
+    stage_of_encoder = {0: 0}
+    for i in range(1, 14):
+        blk = getattr(module, 'conv%d' % i)
+        dw, bn1, a1, pw, bn2, a2 = blk[0], blk[1], blk[2], blk[3], blk[4], blk[5]
+        if _act_of(a1) != _act_of(a2):
+            raise RuntimeError('conv%d: mixed activations are not supported' % i)
+        descs.append(dict(kind=_lib.FD_STAGE_DWPW, c_in=dw.weight.shape[0], c_out=pw.weight.shape[0],
+                          ksize=_sq(dw.kernel_size), stride=_sq(dw.stride), act=_act_of(a1), upsample=0, skip_src=-1))
+        s1, b1 = fold_bn(bn1)
+        s2, b2 = fold_bn(bn2)
+        weights.append((_w(dw).reshape(dw.weight.shape[0], -1), s1, b1,
+                        _w(pw).reshape(pw.weight.shape[0], pw.weight.shape[1]), s2, b2))
+        stage_of_encoder[i] = len(descs) - 1
+        names.append('conv%d' % i)
+    for j in range(1, 6):
+        blk = getattr(module, 'decode_conv%d' % j)
+        (dw, bn1, a1), (pw, bn2, a2) = (blk[0][0], blk[0][1], blk[0][2]), (blk[1][0], blk[1][1], blk[1][2])
+        skip = stage_of_encoder[SKIP_FOR_DECODE[j]] if j in SKIP_FOR_DECODE else -1
+        descs.append(dict(kind=_lib.FD_STAGE_DWPW, c_in=dw.weight.shape[0], c_out=pw.weight.shape[0],
+                          ksize=_sq(dw.kernel_size), stride=1, act=_act_of(a1), upsample=1, skip_src=skip))
+        s1, b1 = fold_bn(bn1)
+        s2, b2 = fold_bn(bn2)
+        weights.append((_w(dw).reshape(dw.weight.shape[0], -1), s1, b1,
+                        _w(pw).reshape(pw.weight.shape[0], pw.weight.shape[1]), s2, b2))
+        names.append('decode_conv%d' % j)
+    hd = module.decode_conv6
+    c, bn, act = hd[0], hd[1], hd[2]
+    descs.append(dict(kind=_lib.FD_STAGE_HEAD, c_in=c.weight.shape[1], c_out=1, ksize=1, stride=1,
+                      act=_act_of(act), upsample=0, skip_src=-1))
+    s, b = fold_bn(bn)
+    weights.append((None, None, None, _w(c).reshape(1, -1), s, b))
+    names.append('decode_conv6')
+    return descs, weights, names
+
+
+def _fp(a):
+    if a is None:
+        return None
+    assert a.dtype == np.float32 and a.flags['C_CONTIGUOUS']
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Plan:
+    """Owns one ``fd_plan`` (fixed N,H,W,dtype,device).  Thin: every method is one C-ABI call."""
+
+    def __init__(self, descs, weights, names, n, h, w, dtype, device_index):
+        self.lib = _lib.load()
+        self.n, self.h, self.w, self.dtype = n, h, w, dtype
+        self.device_index = device_index
+        self.names = list(names)
+        arr = (StageDesc * len(descs))(*[StageDesc(**d) for d in descs])
+        handle = ctypes.c_void_p()
+        _lib.check(self.lib.fd_plan_create(arr, len(descs), n, h, w, DTYPE_CODE[dtype], device_index,
+                                           ctypes.byref(handle)))
+        self.handle = handle
+        self.set_weights(weights)
+
+    @classmethod
+    def from_module(cls, module, n, h, w, dtype, device_index):
+        descs, weights, names = describe(module)
+        return cls(descs, weights, names, n, h, w, dtype, device_index)
+
+    def set_weights(self, weights):
+        for i, wt in enumerate(weights):
+            keep = [np.ascontiguousarray(a, dtype=np.float32) if a is not None else None for a in wt]
+            _lib.check(self.lib.fd_plan_set_stage_weights(self.handle, i, *[_fp(a) for a in keep]))
+
+    def set_option(self, name, value):
+        _lib.check(self.lib.fd_plan_set_option(self.handle, name.encode(), int(value)))
+
+    def get_option(self, name):
+        v = ctypes.c_int()
+        _lib.check(self.lib.fd_plan_get_option(self.handle, name.encode(), ctypes.byref(v)))
+        return v.value
+
+    def forward(self, x, y, stream_ptr):
+        _lib.check(self.lib.fd_forward(self.handle, x.data_ptr(), y.data_ptr(), stream_ptr))
+
+    def forward_host(self, x_host, y_host, stream_ptr):
+        _lib.check(self.lib.fd_forward_host(self.handle, x_host.data_ptr(), y_host.data_ptr(), stream_ptr))
+
+    def launches_per_forward(self):
+        v = ctypes.c_int()
+        _lib.check(self.lib.fd_plan_launches_per_forward(self.handle, ctypes.byref(v)))
+        return v.value
+
+    def workspace_bytes(self):
+        v = ctypes.c_size_t()
+        _lib.check(self.lib.fd_plan_workspace_bytes(self.handle, ctypes.byref(v)))
+        return v.value
+
+    def steps(self):
+        n = ctypes.c_int()
+        _lib.check(self.lib.fd_plan_step_count(self.handle, ctypes.byref(n)))
+        out = []
+        for i in range(n.value):
+            st, ab, mc = ctypes.c_int(), ctypes.c_double(), ctypes.c_double()
+            buf = ctypes.create_string_buffer(96)
+            _lib.check(self.lib.fd_plan_step_info(self.handle, i, ctypes.byref(st), ctypes.byref(ab), ctypes.byref(mc),
+                                                  buf, 96))
+            out.append(dict(step=i, stage=st.value, stage_name=self.names[st.value], kernel=buf.value.decode(),
+                            alg_bytes=ab.value, macs=mc.value))
+        return out
+
+    def time_steps(self, x, y, stream_ptr, warmup=3, iters=20, flush_l2=True):
+        steps = self.steps()
+        ms = (ctypes.c_float * len(steps))()
+        _lib.check(self.lib.fd_plan_time_steps(self.handle, x.data_ptr(), y.data_ptr(), stream_ptr, warmup, iters,
+                                               1 if flush_l2 else 0, ms))
+        for s, t in zip(steps, ms):
+            s['ms'] = float(t)
+        return steps
+
+    def stage_tensor(self, stage, which=0):
+        """NHWC view (torch tensor aliasing plan memory) of a stage buffer, for parity tests."""
+        ptr = ctypes.c_void_p()
+        n, h, w, c, cs = (ctypes.c_int() for _ in range(5))
+        _lib.check(self.lib.fd_stage_buffer(self.handle, stage, which, ctypes.byref(ptr), ctypes.byref(n),
+                                            ctypes.byref(h), ctypes.byref(w), ctypes.byref(c), ctypes.byref(cs)))
+        numel = n.value * h.value * w.value * cs.value
+        return _alias_device_memory(ptr.value, (n.value, h.value, w.value, c.value), numel, self.dtype,
+                                    self.device_index)
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            self.lib.fd_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _CudaArrayView:
+    """Minimal __cuda_array_interface__ wrapper so torch can alias plan-owned memory."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {'data': (ptr, False), 'shape': shape, 'typestr': typestr, 'version': 3,
+                                         'strides': None}
+
+
+def _alias_device_memory(ptr, shape, numel, dtype, device_index):
+    if dtype == torch.float32:
+        with torch.cuda.device(device_index):
+            return torch.as_tensor(_CudaArrayView(ptr, (numel,), '<f4'), device='cuda:%d' % device_index).view(shape)
+    with torch.cuda.device(device_index):
+        raw = torch.as_tensor(_CudaArrayView(ptr, (numel,), '<i2'), device='cuda:%d' % device_index)
+    return raw.view(dtype).view(shape)
+
+
+def metrics_accumulate(pred, target, sums):
+    """fd_metrics_accumulate: per-image metrics of ``pred`` [n,1,h,w] vs ``target`` added into the
+    11-double device vector ``sums`` (reference metrics.py:31-55 per image + AverageMeter sums)."""
+    lib = _lib.load()
+    assert pred.is_cuda and target.is_cuda and sums.is_cuda and sums.dtype == torch.float64 and sums.numel() == N_METRICS
+    pred = pred.contiguous()
+    target = target.contiguous().float()
+    n = pred.shape[0]
+    hw = pred[0].numel()
+    stream = torch.cuda.current_stream(pred.device).cuda_stream
+    _lib.check(lib.fd_metrics_accumulate(pred.data_ptr(), target.data_ptr(), DTYPE_CODE[pred.dtype], n, hw,
+                                         sums.data_ptr(), pred.device.index, stream))

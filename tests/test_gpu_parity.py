@@ -1,0 +1,194 @@
+"""GPU parity tests: the CUDA path (through models.MobileNetSkipAdd -> ctypes -> C-ABI) against the
+oracle and the committed golden vectors.  Tolerances are north_star's: 1e-3 relative for fp32,
+1e-2 for fp16 (bf16, which north_star does not bound, is checked at 4e-2 element-wise -- the
+reference run in bf16 against itself in fp32 shows 6.5e-2, BASELINE.md section 5 -- plus a
+delta1/RMSE agreement check)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_err
+from fastdepth_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-3, torch.float16: 1e-2, torch.bfloat16: 4e-2}
+STAGE_TOL = {torch.float32: 1e-3, torch.float16: 1.5e-2, torch.bfloat16: 6e-2}
+
+
+def oracle():
+    from oracle import fastdepth_oracle as orc
+    return orc
+
+
+def make_model(widths, dtype, hw=(224, 224), seed=1):
+    import models
+    sd = synthetic.synthetic_state_dict(widths, seed=seed)
+    m = models.MobileNetSkipAdd(hw, pretrained=False, widths=widths)
+    m.load_state_dict(sd)
+    return m.eval().cuda().to(dtype), sd
+
+
+def quantised_sd(sd, dtype):
+    """What the reference sees after model.half(): parameters rounded to the storage dtype."""
+    if dtype == torch.float32:
+        return sd
+    return {k: (v.to(dtype).float() if v.is_floating_point() else v) for k, v in sd.items()}
+
+
+def run(m, x, dtype, path):
+    with torch.no_grad():
+        from fastdepth_b200.engine import SkipAddEngine
+        eng = SkipAddEngine(m)
+        eng.set_option('path', path)
+        m.__dict__['_fd_engine'] = eng
+        y = m(x.cuda().to(dtype))
+    torch.cuda.synchronize()
+    return y, eng
+
+
+@pytest.mark.parametrize('name', ['skipadd_stock_2x64x96', 'skipadd_pruned_2x64x96', 'skipadd_stock_1x224x224'])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('path', [0, 1])
+def test_golden_end_to_end(name, dtype, path):
+    fx = np.load(os.path.join(GOLDEN, name + '.npz'))
+    widths = (tuple(int(v) for v in fx['widths_enc']), tuple(int(v) for v in fx['widths_dec']))
+    n, h, w = (int(v) for v in fx['shape'])
+    m, _ = make_model(widths, dtype, (h, w), seed=int(fx['wseed']))
+    x = synthetic.synthetic_input(n, h, w, seed=int(fx['xseed']))
+    y, _ = run(m, x, dtype, path)
+    want = torch.from_numpy(fx['output'])
+    assert y.shape == want.shape and y.dtype == dtype and y.is_contiguous()
+    assert (want == 0).float().mean() < 0.5
+    assert rel_err(y.float().cpu(), want) <= TOL[dtype]
+
+
+@pytest.mark.parametrize('widths', [synthetic.STOCK_WIDTHS, synthetic.PRUNED_WIDTHS], ids=['stock', 'pruned'])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+@pytest.mark.parametrize('path', [0, 1])
+@pytest.mark.parametrize('fold', [0, 1])
+def test_stage_by_stage(widths, dtype, path, fold):
+    """Every named child's output vs the oracle (localises the first diverging stage)."""
+    orc = oracle()
+    m, sd = make_model(widths, dtype, (96, 64))
+    x = synthetic.synthetic_input(3, 96, 64, seed=4)
+    from fastdepth_b200.engine import SkipAddEngine
+    eng = SkipAddEngine(m)
+    eng.set_option('path', path)
+    eng.set_option('fold_head', fold)
+    m.__dict__['_fd_engine'] = eng
+    with torch.no_grad():
+        y = m(x.cuda().to(dtype))
+    torch.cuda.synchronize()
+    stages = {}
+    want = orc.skipadd_forward(quantised_sd(sd, dtype), x.to(dtype).float(), stages=stages)
+    plan = next(iter(eng.plans.values()))
+    for i, name in enumerate(plan.names[:-1]):
+        got = plan.stage_tensor(i).float().cpu().permute(0, 3, 1, 2)
+        ref = stages[name]
+        if fold and name == 'decode_conv5':
+            ref = stages['decode_conv5.pw']            # the folded plan keeps the low-res tensor
+        assert got.shape == ref.shape, name
+        assert rel_err(got, ref) <= STAGE_TOL[dtype], name
+    assert rel_err(y.float().cpu(), want) <= TOL[dtype]
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
+def test_full_size_batch64_properties(dtype):
+    """BASELINE metric config (N=64, 224x224): oracle on a few images + size-independent properties:
+    images are independent (a batch equals its images run alone, bit-exact) and the fused path
+    agrees with the unfused one."""
+    orc = oracle()
+    m, sd = make_model(synthetic.STOCK_WIDTHS, dtype)
+    x = synthetic.synthetic_input(64, 224, 224, seed=9)
+    y1, _ = run(m, x, dtype, 1)
+    y0, _ = run(m, x, dtype, 0)
+    assert rel_err(y1.float().cpu(), y0.float().cpu()) <= TOL[dtype]
+    pick = [0, 31, 63]
+    want = orc.skipadd_forward(quantised_sd(sd, dtype), x[pick].to(dtype).float())
+    assert rel_err(y1[pick].float().cpu(), want) <= TOL[dtype]
+    ys, _ = run(m, x[pick], dtype, 1)
+    assert torch.equal(ys, y1[pick])
+    assert torch.isfinite(y1.float()).all()
+
+
+def test_bf16_metric_agreement():
+    """config 4 is bf16; north_star gives no element-wise bf16 bound, so delta1/RMSE agreement is the
+    binding check."""
+    orc = oracle()
+    m, sd = make_model(synthetic.STOCK_WIDTHS, torch.bfloat16)
+    x = synthetic.synthetic_input(8, 224, 224, seed=2)
+    y, _ = run(m, x, torch.bfloat16, 1)
+    ref = orc.skipadd_forward(sd, x)
+    tgt = synthetic.synthetic_target(ref, seed=1)
+    a, _ = orc.average_per_image(y.float().cpu().numpy(), tgt.numpy())
+    b, _ = orc.average_per_image(ref.numpy(), tgt.numpy())
+    assert abs(a['delta1'] - b['delta1']) < 0.02
+    assert abs(a['rmse'] - b['rmse']) / b['rmse'] < 0.05
+
+
+def test_non_contiguous_input_and_high_res():
+    orc = oracle()
+    m, sd = make_model(synthetic.STOCK_WIDTHS, torch.float16, (480, 640))
+    x = synthetic.synthetic_input(2, 480, 640, seed=3)
+    xt = x.permute(0, 1, 3, 2).contiguous().permute(0, 1, 3, 2)      # same values, exotic strides
+    assert not xt.is_contiguous()
+    y, _ = run(m, xt, torch.float16, 1)
+    want = orc.skipadd_forward(quantised_sd(sd, torch.float16), x.half().float())
+    assert rel_err(y.float().cpu(), want) <= 1e-2
+
+
+def test_error_behaviour():
+    m, _ = make_model(synthetic.STOCK_WIDTHS, torch.float16)
+    with pytest.raises(RuntimeError):                      # reference: size mismatch at the first skip add
+        m(torch.rand(1, 3, 228, 304, device='cuda', dtype=torch.float16))
+    with pytest.raises(RuntimeError, match='should be the same'):
+        m(torch.rand(1, 3, 64, 64, device='cuda', dtype=torch.float32))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        m(torch.rand(1, 3, 64, 64).half())
+
+
+def test_weight_update_is_picked_up():
+    m, sd = make_model(synthetic.STOCK_WIDTHS, torch.float32, (64, 64))
+    x = synthetic.synthetic_input(1, 64, 64, seed=1).cuda()
+    with torch.no_grad():
+        a = m(x).clone()
+        m.load_state_dict(synthetic.synthetic_state_dict(seed=5))
+        b = m(x)
+    want = oracle().skipadd_forward(synthetic.synthetic_state_dict(seed=5), x.cpu())
+    assert not torch.allclose(a, b) and rel_err(b.cpu(), want) <= 1e-3
+
+
+def test_metrics_kernel_known_answer():
+    from fastdepth_b200 import evaluate, plan
+    fx = np.load(os.path.join(GOLDEN, 'metrics_known_answer.npz'))
+    names = [str(n) for n in fx['names']]
+    sums = evaluate.new_sums('cuda')
+    plan.metrics_accumulate(torch.from_numpy(fx['multi_out']).cuda(), torch.from_numpy(fx['multi_tgt']).cuda(), sums)
+    avg = evaluate.finalize(sums)
+    assert avg['count'] == 3
+    for k, v in zip(names, fx['multi_avg']):
+        assert avg[k] == pytest.approx(float(v), rel=5e-5), k
+    sums.zero_()
+    p = torch.from_numpy(fx['pred_sub4']).cuda().view(1, 1, 56, 56)
+    t = torch.from_numpy(fx['depth_sub4']).cuda().view(1, 1, 56, 56)
+    plan.metrics_accumulate(p, t, sums)
+    one = evaluate.finalize(sums)
+    for k, v in zip(names, fx['sub4_values']):
+        assert one[k] == pytest.approx(float(v), rel=5e-5), k
+
+
+def test_sharded_evaluate_single_gpu():
+    from fastdepth_b200 import evaluate
+    orc = oracle()
+    m, sd = make_model(synthetic.STOCK_WIDTHS, torch.float32, (64, 96))
+    x = synthetic.synthetic_input(6, 64, 96, seed=8)
+    ref = orc.skipadd_forward(sd, x)
+    tgt = synthetic.synthetic_target(ref, seed=2)
+    got = evaluate.evaluate(m, [(x[:4], tgt[:4]), (x[4:], tgt[4:])], torch.device('cuda:0'))
+    want, n = orc.average_per_image(ref.numpy(), tgt.numpy())
+    assert got['count'] == n
+    for k in ('rmse', 'mae', 'delta1', 'absrel', 'lg10'):
+        assert got[k] == pytest.approx(want[k], rel=2e-3, abs=1e-4), k

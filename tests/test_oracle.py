@@ -1,0 +1,78 @@
+"""Pin the oracle (oracle/fastdepth_oracle.py) against vectors the LIVE reference produced
+(tests/golden/make_golden.py ran reference models.py:654-732 and metrics.py:31-95)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_err
+from fastdepth_b200 import synthetic
+from oracle import fastdepth_oracle as orc
+
+FIXTURES = ['skipadd_stock_2x64x96', 'skipadd_pruned_2x64x96', 'skipadd_stock_1x224x224']
+
+
+def _load(name):
+    return np.load(os.path.join(GOLDEN, name + '.npz'))
+
+
+@pytest.mark.parametrize('name', FIXTURES)
+def test_oracle_forward_matches_reference(name):
+    fx = _load(name)
+    widths = (tuple(int(v) for v in fx['widths_enc']), tuple(int(v) for v in fx['widths_dec']))
+    n, h, w = (int(v) for v in fx['shape'])
+    sd = synthetic.synthetic_state_dict(widths, seed=int(fx['wseed']))
+    x = synthetic.synthetic_input(n, h, w, seed=int(fx['xseed']))
+    stages = {}
+    y = orc.skipadd_forward(sd, x, stages=stages)
+    want = torch.from_numpy(fx['output'])
+    assert y.shape == want.shape
+    assert (want == 0).float().mean() < 0.5          # not a dead output
+    assert rel_err(y, want) < 1e-4              # fp32 summation-order drift only (fp64 tie-break below)
+    # stage-wise samples localise any drift
+    for key in [k[6:-4] for k in fx.files if k.startswith('stage/') and k.endswith('/idx')]:
+        got = stages[key].reshape(-1)[torch.from_numpy(fx['stage/%s/idx' % key])]
+        ref = torch.from_numpy(fx['stage/%s/val' % key])
+        assert tuple(stages[key].shape) == tuple(fx['stage/%s/shape' % key]), key
+        assert torch.allclose(got, ref, rtol=3e-4, atol=3e-4), key    # fp32 summation-order drift
+
+
+def test_oracle_fp64_agrees_with_fp32():
+    sd = synthetic.synthetic_state_dict(seed=3)
+    x = synthetic.synthetic_input(1, 32, 64, seed=5)
+    a = orc.skipadd_forward(sd, x)
+    b = orc.skipadd_forward(sd, x, dtype=torch.float64)
+    assert rel_err(a, b) < 1e-4
+
+
+def test_relu6_clamp_is_exercised():
+    """The synthetic recipe must actually hit the upper clamp, otherwise ReLU6 is untested."""
+    sd = synthetic.synthetic_state_dict(seed=1)
+    x = synthetic.synthetic_input(1, 64, 64, seed=0)
+    stages = {}
+    orc.skipadd_forward(sd, x, stages=stages)
+    sat = (stages['conv5'] >= 6.0).float().mean().item()
+    assert 0.005 < sat < 0.5
+
+
+def test_metrics_known_answer():
+    fx = _load('metrics_known_answer')
+    names = [str(n) for n in fx['names']]
+    got = orc.evaluate_one(fx['pred_sub4'], fx['depth_sub4'])
+    for k, v in zip(names, fx['sub4_values']):
+        assert got[k] == pytest.approx(float(v), rel=2e-5, abs=1e-9), k
+    full = dict(zip(names, fx['full_values']))
+    assert full['rmse'] == pytest.approx(618.001, abs=2e-3)
+    assert full['delta1'] == pytest.approx(0.7773, abs=1e-4)
+
+
+def test_metrics_are_averaged_per_image():
+    fx = _load('metrics_known_answer')
+    names = [str(n) for n in fx['names']]
+    avg, n = orc.average_per_image(fx['multi_out'], fx['multi_tgt'])
+    assert n == 3
+    for k, v in zip(names, fx['multi_avg']):
+        assert avg[k] == pytest.approx(float(v), rel=2e-5), k
+    pooled = orc.evaluate_one(fx['multi_out'], fx['multi_tgt'])
+    assert abs(pooled['rmse'] - avg['rmse']) > 1e-3              # pooling pixels is a different number
