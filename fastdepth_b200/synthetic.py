@@ -5,15 +5,15 @@ no network, so every measurement here uses random-init weights of the named arch
 Plain default init collapses activations to ~1e-3 and makes relative-error parity vacuous
 (SURVEY.md section 4 "synthetic-weight pitfalls"), hence this recipe:
 
-* conv weights: encoder N(0, sqrt(2/(k*k*Cout))) as ``weights_init`` would (reference
-  models.py:36-41); decoder U(-b, b), b = 1/sqrt(fan_in) (PyTorch default, which the SkipAdd
-  decoder keeps because of the ``weights_init``-on-Sequential no-op, reference models.py:699-704);
-* BN: running_mean ~ N(0, 0.1), running_var ~ U(0.25, 0.75), gamma ~ U(0.5, 3), beta ~ N(0.2, 0.3);
-  per-block gain re-normalisation keeps activations alive through 20 stages;
-* last BN (decode_conv6): gamma = 1, beta = 0.5 so the final ReLU is not identically zero.
+* conv weights: encoder N(0, sqrt(2/fan_in)); decoder U(-b, b), b = 1/sqrt(fan_in) (PyTorch default,
+  which the SkipAdd decoder keeps because of the ``weights_init``-on-Sequential no-op, reference
+  models.py:699-704); the head's weights are made positive so the output is depth-like;
+* BN: gamma ~ U(0.25, 0.75) (2 % hot channels U(2.5, 3.5)), beta ~ N(0.6, 0.25); running_mean / running_var CALIBRATED on a seeded probe
+  batch (what a trained checkpoint carries) -- see ``synthetic_state_dict``;
+* last BN (decode_conv6): gamma = 1, beta = 3 so the final ReLU leaves a live, metres-like map.
 
-Everything is drawn from ``numpy.random.Generator(PCG64(seed))`` in a fixed order, so the values
-are identical on every machine and torch version (the golden fixtures depend on that).
+Random draws come from ``numpy.random.Generator(PCG64(seed))`` in a fixed order and the calibration
+runs in fp64, so the fp32 values are reproducible across machines (the golden fixtures depend on it).
 """
 import numpy as np
 import torch
@@ -30,54 +30,95 @@ STOCK_DECODER = (512, 256, 128, 64, 32)
 STOCK_WIDTHS = (STOCK_ENCODER, STOCK_DECODER)
 
 
-def _bn(rng, c, out, prefix, last=False):
-    if last:
-        gamma = np.ones(c); beta = np.full(c, 0.5)
-        mean = rng.normal(0.0, 0.05, c); var = rng.uniform(0.5, 0.75, c)
-    else:
-        gamma = rng.uniform(0.5, 3.0, c); beta = rng.normal(0.2, 0.3, c)
-        mean = rng.normal(0.0, 0.1, c); var = rng.uniform(0.25, 0.75, c)
-    out[prefix + '.weight'] = gamma.astype(np.float32)
-    out[prefix + '.bias'] = beta.astype(np.float32)
-    out[prefix + '.running_mean'] = mean.astype(np.float32)
-    out[prefix + '.running_var'] = var.astype(np.float32)
-    out[prefix + '.num_batches_tracked'] = np.asarray(0, dtype=np.int64)
+_CACHE = {}
 
 
-def synthetic_state_dict(widths=STOCK_WIDTHS, seed=1, gain=1.0):
+# Conditioning knobs, tuned in round 1 (see DESIGN.md 'synthetic weights'): a random BN+ReLU network is
+# chaotic for E[gamma^2] >~ 1 -- the reference's OWN fp16 forward then differs from its fp32 forward by
+# 2-9 % and a 1e-2 criterion is noise.  With these values the fp16 storage noise reaches the output at
+# ~4e-3 max / 7e-4 mean while a 5 % weight error in conv7 still moves the output by ~1 % mean / 10 % max.
+GAMMA_RANGE = (0.25, 0.75)
+BETA = (0.6, 0.25)
+HOT = (0.02, 2.5, 3.5)      # fraction of encoder channels with a large gamma (drives the ReLU6 clamp)
+
+
+def synthetic_state_dict(widths=STOCK_WIDTHS, seed=1, calib_hw=(96, 128)):
     """state_dict (torch fp32 CPU tensors) with the MobileNetSkipAdd key schema
-    (SURVEY.md section 8a-a2)."""
+    (SURVEY.md section 8a-a2).
+
+    BatchNorm running statistics are CALIBRATED: a seeded probe batch is pushed through the
+    layers (fp64, torch CPU) and every BN's running_mean/var are set to the statistics of the
+    tensor it normalises -- what training leaves behind in a real checkpoint.  That keeps the
+    network well conditioned (fp16 storage noise is not chaotically amplified), so the 1e-2 fp16
+    tolerance is a meaningful bound and not noise.  gamma ~ U(0.25, 0.75) with 2 % "hot" encoder
+    channels at U(2.5, 3.5) that drive ~0.1 % of the activations into the ReLU6 clamp;
+    beta ~ N(0.6, 0.25) leaves ~10-15 % exact zeros after each ReLU."""
+    key = (tuple(widths[0]), tuple(widths[1]), int(seed), tuple(calib_hw), GAMMA_RANGE, BETA, HOT)
+    if key in _CACHE:
+        return {k: v.clone() for k, v in _CACHE[key].items()}
+    import torch.nn.functional as F
     enc, dec = widths
     rng = np.random.Generator(np.random.PCG64(seed))
     sd = {}
+    f64 = torch.float64
 
-    def gauss(shape, k, c_out, g):
-        return (rng.normal(0.0, g * np.sqrt(2.0 / (k * k * c_out)), shape)).astype(np.float32)
+    def gauss(shape, fan):
+        return torch.from_numpy(rng.normal(0.0, np.sqrt(2.0 / fan), shape))
 
-    def unif(shape, fan_in, g):
-        b = g / np.sqrt(fan_in)
-        return rng.uniform(-b, b, shape).astype(np.float32)
+    def unif(shape, fan):
+        b = 1.0 / np.sqrt(fan)
+        return torch.from_numpy(rng.uniform(-b, b, shape))
 
-    # stem: conv0.0 / conv0.1
-    sd['conv0.0.weight'] = gauss((enc[0], 3, 3, 3), 3, enc[0], 3.0 * gain)
-    _bn(rng, enc[0], sd, 'conv0.1')
+    def bn_act(t, c, prefix, hi, last=False):
+        """draw gamma/beta, calibrate mean/var on t, store, apply BN + clamp"""
+        if last:
+            gamma = np.ones(c); beta = np.full(c, 3.0)          # depth-like, strictly alive head
+        else:
+            gamma = rng.uniform(GAMMA_RANGE[0], GAMMA_RANGE[1], c); beta = rng.normal(BETA[0], BETA[1], c)
+            hot = rng.random(c) < HOT[0]
+            gamma = np.where(hot & (hi is not None), rng.uniform(HOT[1], HOT[2], c), gamma)
+        mean = t.mean(dim=(0, 2, 3)); var = t.var(dim=(0, 2, 3), unbiased=False)
+        sd[prefix + '.weight'] = torch.from_numpy(gamma).float()
+        sd[prefix + '.bias'] = torch.from_numpy(beta).float()
+        sd[prefix + '.running_mean'] = mean.float()
+        sd[prefix + '.running_var'] = var.float()
+        sd[prefix + '.num_batches_tracked'] = torch.zeros((), dtype=torch.int64)
+        g, b = sd[prefix + '.weight'].to(f64), sd[prefix + '.bias'].to(f64)
+        m, v = sd[prefix + '.running_mean'].to(f64), sd[prefix + '.running_var'].to(f64)
+        inv = g / torch.sqrt(v + 1e-5)
+        y = t * inv.view(1, -1, 1, 1) + (b - m * inv).view(1, -1, 1, 1)
+        return y.clamp(0.0, hi) if hi is not None else y.clamp_min(0.0)
+
+    def put(name, wt):
+        sd[name] = wt.float().contiguous()
+        return sd[name].to(f64)
+
+    strides = (2, 1, 2, 1, 2, 1, 2, 1, 1, 1, 1, 1, 2, 1)
+    x = torch.from_numpy(np.random.Generator(np.random.PCG64(seed + 7919)).random((2, 3) + tuple(calib_hw)))
+    x = bn_act(F.conv2d(x, put('conv0.0.weight', gauss((enc[0], 3, 3, 3), 27)), None, 2, 1), enc[0], 'conv0.1', 6.0)
+    keep = {}
     for i in range(1, 14):
-        c_in, c_out = enc[i - 1], enc[i]
-        # depthwise fan-in is 9: weights_init's sqrt(2/(9*C)) starves it, so lift the gain
-        sd['conv%d.0.weight' % i] = gauss((c_in, 1, 3, 3), 3, c_in, gain * np.sqrt(c_in) * 0.5)
-        _bn(rng, c_in, sd, 'conv%d.1' % i)
-        sd['conv%d.3.weight' % i] = gauss((c_out, c_in, 1, 1), 1, c_out, 0.6 * gain * np.sqrt(c_out / c_in))
-        _bn(rng, c_out, sd, 'conv%d.4' % i)
+        ci, co = enc[i - 1], enc[i]
+        x = bn_act(F.conv2d(x, put('conv%d.0.weight' % i, gauss((ci, 1, 3, 3), 9)), None, strides[i], 1, 1, ci),
+                   ci, 'conv%d.1' % i, 6.0)
+        x = bn_act(F.conv2d(x, put('conv%d.3.weight' % i, gauss((co, ci, 1, 1), ci))), co, 'conv%d.4' % i, 6.0)
+        if i in (1, 3, 5):
+            keep[i] = x
     c = enc[13]
-    for j, c_out in enumerate(dec, start=1):
-        sd['decode_conv%d.0.0.weight' % j] = unif((c, 1, 5, 5), 25, 0.8 * gain)
-        _bn(rng, c, sd, 'decode_conv%d.0.1' % j)
-        sd['decode_conv%d.1.0.weight' % j] = unif((c_out, c, 1, 1), c, 0.9 * gain)
-        _bn(rng, c_out, sd, 'decode_conv%d.1.1' % j)
-        c = c_out
-    sd['decode_conv6.0.weight'] = np.abs(unif((1, c, 1, 1), c, 1.5 * gain))   # positive head: depth-like, not half-dead
-    _bn(rng, 1, sd, 'decode_conv6.1', last=True)
-    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
+    add_after = {4: 1, 3: 3, 2: 5}
+    for j, co in enumerate(dec, start=1):
+        x = bn_act(F.conv2d(x, put('decode_conv%d.0.0.weight' % j, unif((c, 1, 5, 5), 25)), None, 1, 2, 1, c),
+                   c, 'decode_conv%d.0.1' % j, None)
+        x = bn_act(F.conv2d(x, put('decode_conv%d.1.0.weight' % j, unif((co, c, 1, 1), c))), co,
+                   'decode_conv%d.1.1' % j, None)
+        x = x.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+        if j in add_after:
+            x = x + keep[add_after[j]]
+        c = co
+    bn_act(F.conv2d(x, put('decode_conv6.0.weight', unif((1, c, 1, 1), c).abs())), 1, 'decode_conv6.1', None, last=True)
+    # keep the reference's key order (conv.weight first, then BN entries)
+    _CACHE[key] = sd
+    return {k: v.clone() for k, v in sd.items()}
 
 
 def synthetic_input(n, h, w, seed=0):

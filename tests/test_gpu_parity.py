@@ -1,8 +1,13 @@
 """GPU parity tests: the CUDA path (through models.MobileNetSkipAdd -> ctypes -> C-ABI) against the
 oracle and the committed golden vectors.  Tolerances are north_star's: 1e-3 relative for fp32,
-1e-2 for fp16 (bf16, which north_star does not bound, is checked at 4e-2 element-wise -- the
-reference run in bf16 against itself in fp32 shows 6.5e-2, BASELINE.md section 5 -- plus a
-delta1/RMSE agreement check)."""
+1e-2 for fp16, both against the reference forward evaluated in fp32 (golden vectors from the live
+reference, or the pinned oracle on the same storage-dtype-representable parameters and inputs).
+bf16, which north_star does not bound, is checked at 1e-1 element-wise (8 mantissa bits: the same
+storage roundings emulated on the CPU give 3.5e-2 on these weights; the reference run in bf16
+against itself in fp32 shows 6.5e-2) plus a delta1/RMSE agreement check.
+The synthetic weights are conditioned so that the numbers mean something: see
+fastdepth_b200/synthetic.py (a random BN+ReLU net is otherwise chaotic and even the reference's own
+fp16 forward is 2-9 % away from its fp32 forward)."""
 import os
 
 import numpy as np
@@ -14,8 +19,8 @@ from fastdepth_b200 import synthetic
 
 pytestmark = pytest.mark.gpu
 
-TOL = {torch.float32: 1e-3, torch.float16: 1e-2, torch.bfloat16: 4e-2}
-STAGE_TOL = {torch.float32: 1e-3, torch.float16: 1.5e-2, torch.bfloat16: 6e-2}
+TOL = {torch.float32: 1e-3, torch.float16: 1e-2, torch.bfloat16: 1e-1}
+STAGE_TOL = {torch.float32: 1e-3, torch.float16: 1e-2, torch.bfloat16: 1e-1}
 
 
 def oracle():
