@@ -31,7 +31,7 @@ struct BlockTcPlan;   // opaque per-stage state (tensor maps, tile config)
 bool block_tc_supported(int dtype, const StageGeom& g, bool head_fused);
 int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float head_scale, float head_bias, int head_act,
                      void* head_out, BlockTcPlan** out);
-int block_tc_launch(BlockTcPlan* p, cudaStream_t st);
+int block_tc_launch(BlockTcPlan* p, cudaStream_t st, void* head_out);
 void block_tc_destroy(BlockTcPlan* p);
 const char* block_tc_name(BlockTcPlan* p);
 
@@ -144,6 +144,7 @@ static int build_steps(fd_plan* p) {
     // decode_conv6 below the last upsample: exact because a 1x1 conv, a per-channel affine and ReLU
     // act pixel-wise and nearest upsampling only replicates pixels.
     const bool fold = p->opt_fold_head && last.d.kind == FD_STAGE_DWPW && last.d.upsample && last.d.skip_src < 0;
+    bool head_fused = false;
 
     for (int i = 0; i < ns; ++i) {
         Stage& s = p->stages[i];
@@ -179,18 +180,21 @@ static int build_steps(fd_plan* p) {
                                    (double)s.g.c_in * s.g.c_out * es + 2.0 * s.g.c_out * 4;
             const double fused_bytes = (px_in * s.g.c_in + px_out * up * s.g.c_out * (a.skip ? 2.0 : 1.0)) * es + w_bytes;
             const int dtype = p->dtype;
+            const bool fuse_head = folded_here && p->opt_path == 1 && block_tc_supported(dtype, a.g, true);
             bool use_tc = p->opt_path == 1 && block_tc_supported(dtype, a.g, false);
             if (use_tc) {
-                int rc = block_tc_prepare(dtype, a, nullptr, 0.f, 0.f, 0, nullptr, &s.tc);
+                int rc = fuse_head ? block_tc_prepare(dtype, a, head.pw_w_f32, head.head_scale, head.head_bias, head.g.act, nullptr, &s.tc)
+                                   : block_tc_prepare(dtype, a, nullptr, 0.f, 0.f, 0, nullptr, &s.tc);
                 if (rc != FD_OK) return rc;
                 Step st;
                 st.stage = i;
                 st.name = block_tc_name(s.tc);
-                st.macs = dw_macs + pw_macs;
-                st.alg_bytes = fused_bytes;
+                st.macs = dw_macs + pw_macs + (fuse_head ? px_out * s.g.c_out : 0.0);
+                st.alg_bytes = fuse_head ? (px_in * s.g.c_in + px_out * 4.0) * es + w_bytes + s.g.c_out * 4.0 : fused_bytes;
                 BlockTcPlan* tc = s.tc;
-                st.run = [tc](cudaStream_t stream, const void*, void*) { return block_tc_launch(tc, stream); };
+                st.run = [tc](cudaStream_t stream, const void*, void* y) { return block_tc_launch(tc, stream, y); };
                 p->steps.push_back(st);
+                head_fused = fuse_head;
             } else {
                 Step d;
                 d.stage = i;
@@ -208,7 +212,7 @@ static int build_steps(fd_plan* p) {
                 q.run = [a, dtype](cudaStream_t stream, const void*, void*) { return launch_pw(dtype, a, stream); };
                 p->steps.push_back(q);
             }
-        } else {  // HEAD
+        } else if (!head_fused) {  // HEAD (unless decode_conv6 already ran inside the last block's epilogue)
             const bool up = fold;
             const int hh = up ? last.g.h_out : s.g.h_in, ww = up ? last.g.w_out : s.g.w_in;
             const long long m_total = (long long)s.g.n * hh * ww;

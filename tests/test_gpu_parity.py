@@ -20,7 +20,9 @@ from fastdepth_b200 import synthetic
 pytestmark = pytest.mark.gpu
 
 TOL = {torch.float32: 1e-3, torch.float16: 1e-2, torch.bfloat16: 1e-1}
-STAGE_TOL = {torch.float32: 1e-3, torch.float16: 1e-2, torch.bfloat16: 1e-1}
+# intermediate tensors (bug localisation only): the 2 % 'hot' BN channels (gamma up to 3.5) amplify the
+# storage noise of single elements ~4x before the next layers average it out again
+STAGE_TOL = {torch.float32: 1e-3, torch.float16: 4e-2, torch.bfloat16: 3e-1}
 
 
 def oracle():
