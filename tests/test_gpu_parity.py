@@ -96,6 +96,8 @@ def test_stage_by_stage(widths, dtype, path, fold):
         got = plan.stage_tensor(i).float().cpu().permute(0, 3, 1, 2)
         ref = stages[name]
         if fold and name == 'decode_conv5':
+            if path == 1 and dtype != torch.float32:
+                continue                               # head fused into the block: never materialised
             ref = stages['decode_conv5.pw']            # the folded plan keeps the low-res tensor
         assert got.shape == ref.shape, name
         assert rel_err(got, ref) <= STAGE_TOL[dtype], name
