@@ -30,10 +30,19 @@ int launch_metrics(int dtype, const void* pred, const float* target, int n, int 
 struct BlockTcPlan;   // opaque per-stage state (tensor maps, tile config)
 bool block_tc_supported(int dtype, const StageGeom& g, bool head_fused);
 int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float head_scale, float head_bias, int head_act,
-                     void* head_out, BlockTcPlan** out);
+                     void* head_out, bool tma_epilogue, BlockTcPlan** out);
 int block_tc_launch(BlockTcPlan* p, cudaStream_t st, void* head_out);
 void block_tc_destroy(BlockTcPlan* p);
 const char* block_tc_name(BlockTcPlan* p);
+int block_tc_trace(BlockTcPlan* bp, cudaStream_t st, void* head_out, unsigned long long* out_host, int* rows, int* cols);
+// tensor-core stem (fd_stem_tc.cu)
+struct StemTcPlan;
+bool stem_tc_supported(int dtype, const StageGeom& g);
+int stem_tc_prepare(int dtype, const StageGeom& g, const float* w27_dev, const float* scale_dev, const float* bias_dev, void* out,
+                    StemTcPlan** res);
+int stem_tc_launch(StemTcPlan* sp, const void* x, cudaStream_t st);
+void stem_tc_destroy(StemTcPlan* sp);
+const char* stem_tc_name(StemTcPlan* sp);
 
 static size_t dtype_size(int dtype) { return dtype == FD_F32 ? 4 : 2; }
 
@@ -42,6 +51,7 @@ struct Stage {
     StageGeom g{};
     int out_h = 0, out_w = 0;            // spatial size of the stage's output buffer (after upsample)
     void* out = nullptr;                 // NHWC [n,out_h,out_w,c_out]   (STEM/DWPW)
+    void* out_eff = nullptr;             // buffer the stage really writes (== a skip source when accumulating in place)
     void* mid = nullptr;                 // NHWC [n,h_out,w_out,c_in]     (DWPW, path 0)
     float* dw_w = nullptr;               // [k*k][c_in]
     float* dw_scale = nullptr;
@@ -53,6 +63,7 @@ struct Stage {
     float head_scale = 0.f, head_bias = 0.f;
     bool have_weights = false;
     BlockTcPlan* tc = nullptr;
+    StemTcPlan* stc = nullptr;
 };
 
 struct Step {
@@ -71,7 +82,7 @@ struct fd_plan {
     std::vector<Stage> stages;
     std::vector<Step> steps;
     bool steps_valid = false;
-    int opt_path = 1, opt_fold_head = 1, opt_graph = 1;
+    int opt_path = 1, opt_fold_head = 1, opt_graph = 1, opt_tma_epilogue = 1, opt_inplace_skip = 1;
     size_t workspace_bytes = 0;
     void* stage_x = nullptr;             // device staging for fd_forward_host
     void* stage_y = nullptr;
@@ -112,8 +123,10 @@ static void invalidate(fd_plan* p) {
     p->steps.clear();
     for (auto& g : p->graphs) cudaGraphExecDestroy(g.exec);
     p->graphs.clear();
-    for (auto& s : p->stages)
+    for (auto& s : p->stages) {
         if (s.tc) { block_tc_destroy(s.tc); s.tc = nullptr; }
+        if (s.stc) { stem_tc_destroy(s.stc); s.stc = nullptr; }
+    }
 }
 
 // fp32 host array -> device array of the plan dtype (exact when the values came from that dtype)
@@ -148,7 +161,8 @@ static int build_steps(fd_plan* p) {
 
     for (int i = 0; i < ns; ++i) {
         Stage& s = p->stages[i];
-        const void* in = i > 0 ? p->stages[i - 1].out : nullptr;
+        const void* in = i > 0 ? p->stages[i - 1].out_eff : nullptr;
+        s.out_eff = s.out;
         if (s.d.kind == FD_STAGE_STEM) {
             Step st;
             st.stage = i;
@@ -158,9 +172,17 @@ static int build_steps(fd_plan* p) {
                            29.0 * s.g.c_out * 4;
             Stage* sp = &s;
             const int dtype = p->dtype;
-            st.run = [sp, dtype](cudaStream_t stream, const void* x, void*) {
-                return launch_stem(dtype, x, sp->out, sp->pw_w_f32, sp->pw_scale, sp->pw_bias, sp->g, stream);
-            };
+            if (p->opt_path == 1 && stem_tc_supported(dtype, s.g)) {
+                int rc = stem_tc_prepare(dtype, s.g, s.pw_w_f32, s.pw_scale, s.pw_bias, s.out, &s.stc);
+                if (rc != FD_OK) return rc;
+                st.name = stem_tc_name(s.stc);
+                StemTcPlan* stc = s.stc;
+                st.run = [stc](cudaStream_t stream, const void* x, void*) { return stem_tc_launch(stc, x, stream); };
+            } else {
+                st.run = [sp, dtype](cudaStream_t stream, const void* x, void*) {
+                    return launch_stem(dtype, x, sp->out, sp->pw_w_f32, sp->pw_scale, sp->pw_bias, sp->g, stream);
+                };
+            }
             p->steps.push_back(st);
         } else if (s.d.kind == FD_STAGE_DWPW) {
             BlockArgs a{};
@@ -170,7 +192,7 @@ static int build_steps(fd_plan* p) {
             a.in = in;
             a.mid = s.mid;
             a.out = s.out;
-            a.skip = s.d.skip_src >= 0 ? p->stages[s.d.skip_src].out : nullptr;
+            a.skip = s.d.skip_src >= 0 ? p->stages[s.d.skip_src].out_eff : nullptr;
             a.dw_w = s.dw_w; a.dw_scale = s.dw_scale; a.dw_bias = s.dw_bias;
             a.pw_w = s.pw_w; a.pw_scale = s.pw_scale; a.pw_bias = s.pw_bias;
             const double px_in = (double)s.g.n * s.g.h_in * s.g.w_in, px_out = (double)s.g.n * s.g.h_out * s.g.w_out;
@@ -183,8 +205,12 @@ static int build_steps(fd_plan* p) {
             const bool fuse_head = folded_here && p->opt_path == 1 && block_tc_supported(dtype, a.g, true);
             bool use_tc = p->opt_path == 1 && block_tc_supported(dtype, a.g, false);
             if (use_tc) {
-                int rc = fuse_head ? block_tc_prepare(dtype, a, head.pw_w_f32, head.head_scale, head.head_bias, head.g.act, nullptr, &s.tc)
-                                   : block_tc_prepare(dtype, a, nullptr, 0.f, 0.f, 0, nullptr, &s.tc);
+                // decoder blocks with a skip accumulate INTO the skip tensor (TMA reduce-add): that buffer becomes the
+                // block's output and the skip never has to be read by the SM
+                const bool tma_epi = p->opt_tma_epilogue != 0;
+                if (tma_epi && p->opt_inplace_skip && a.skip != nullptr) { a.out = const_cast<void*>(a.skip); s.out_eff = a.out; }
+                int rc = fuse_head ? block_tc_prepare(dtype, a, head.pw_w_f32, head.head_scale, head.head_bias, head.g.act, nullptr, false, &s.tc)
+                                   : block_tc_prepare(dtype, a, nullptr, 0.f, 0.f, 0, nullptr, tma_epi && (a.skip == nullptr || a.skip == a.out), &s.tc);
                 if (rc != FD_OK) return rc;
                 Step st;
                 st.stage = i;
@@ -381,6 +407,8 @@ static int* option_slot(fd_plan* p, const char* name) {
     if (!strcmp(name, "path")) return &p->opt_path;
     if (!strcmp(name, "fold_head")) return &p->opt_fold_head;
     if (!strcmp(name, "graph")) return &p->opt_graph;
+    if (!strcmp(name, "tma_epilogue")) return &p->opt_tma_epilogue;
+    if (!strcmp(name, "inplace_skip")) return &p->opt_inplace_skip;
     return nullptr;
 }
 
@@ -470,7 +498,7 @@ int fd_stage_buffer(fd_plan* p, int stage, int which, void** dev_ptr, int* n, in
     int hh, ww, cc;
     void* ptr;
     if (which == 0) {
-        ptr = s.out; hh = s.out_h; ww = s.out_w; cc = s.g.c_out;
+        ptr = s.out_eff ? s.out_eff : s.out; hh = s.out_h; ww = s.out_w; cc = s.g.c_out;
         // with decode_conv6 folded below the last upsample the last block writes its low-res output
         if (p->opt_fold_head && stage == (int)p->stages.size() - 2 && s.d.upsample && s.d.skip_src < 0) { hh = s.g.h_out; ww = s.g.w_out; }
     } else if (which == 1) {
@@ -557,6 +585,16 @@ int fd_plan_time_steps(fd_plan* p, const void* x_dev, void* y_dev, void* stream,
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return rc;
+}
+
+int fd_plan_trace_stage(fd_plan* p, int stage, void* y_dev, void* stream, unsigned long long* out_host, int cap, int* rows, int* cols) {
+    if (!p || stage < 0 || stage >= (int)p->stages.size() || !out_host || !rows || !cols) return fail(FD_ERR_INVALID, "bad argument");
+    DeviceGuard guard(p->device);
+    int rc = ensure_steps(p);
+    if (rc) return rc;
+    if (!p->stages[stage].tc) return fail(FD_ERR_STATE, "stage does not run the fused block kernel");
+    if (cap < 8 * 256) return fail(FD_ERR_INVALID, "trace buffer too small (need 2048 entries)");
+    return block_tc_trace(p->stages[stage].tc, (cudaStream_t)stream, y_dev, out_host, rows, cols);
 }
 
 int fd_metrics_accumulate(const void* pred_dev, const float* target_dev, int dtype, int n, int hw, double* sums_dev,

@@ -28,7 +28,7 @@
 #include <new>
 #include <string>
 
-#include "fd_common.cuh"
+#include "fd_tc_common.cuh"
 
 namespace fd {
 
@@ -41,6 +41,7 @@ constexpr int TC_THREADS = (TC_WARP_MMA + 1) * 32;           // 576
 constexpr int TC_KBLK = 64;                     // channels per K-block (one 128-byte swizzle row)
 constexpr int TC_A_STAGE_BYTES = 128 * 128;     // 128 rows x 64 x 2 B
 constexpr int TC_MAX_IN = 6, TC_MAX_A = 4, TC_MAX_B = 16;
+constexpr int TC_TRACE_N = 256;
 
 struct TcParams {
     int n, h_in, w_in, h_out, w_out, c_in, c_out;
@@ -66,143 +67,15 @@ struct TcParams {
     int in_stage_stride;  // in_stage_bytes + dw parameter block, rounded to 128
     int dwp_bytes;        // bytes of one K-block's depthwise parameter block
     int cpad_all;         // n_cta * splits: padded length of the pointwise BN vectors
+    int n_stg;            // epilogue staging buffers (16 KB each): 2, or 1 when shared memory is tight
+    int epi_tma;          // 1: staging tiles leave through TMA tensor stores (4 strided views for nearest-x2 upsampling)
+    int epi_red;          // 1: ... as element-wise ADD into the skip tensor, which then IS the block's output (in place)
+    unsigned long long mg_splits, mg_tx, mg_ty;   // 2^40 / d reciprocals for the item -> tile decode
     const void* dwp;      // [kblocks] x { [k*k][64] 16-bit taps, [64] fp32 scale, [64] fp32 bias }
-    const float* pw_scale;
-    const float* pw_bias; // [cpad_all]
+                          //   (scale and bias pre-divided by 6 for ReLU6 stages: y = 6 * sat(acc*s/6 + b/6))
+    const float2* pw_affine;  // [cpad_all] (scale, bias) pairs, same /6 convention
     const float* head_w;  // [cpad_all]
-};
-
-// ----------------------------------------------------------------------------------------------
-// PTX wrappers
-// ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-// plain (non-tensor) bulk copy global -> shared, completion on an mbarrier (SASS UBLKCP)
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, both operands K-major, 16-bit inputs, fp32 accumulate
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc),
-        "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr) : "memory");
-}
-// 32 consecutive columns of this thread's TMEM lane, load + wait in ONE asm statement so that no use of the
-// destination registers can be scheduled before tcgen05.wait::ld
-__device__ __forceinline__ void tmem_ld32_sync(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16_sync(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 UMMA): start address >> 4, LBO (unused for
-// swizzled K-major) = 1, SBO = 1024 B between 8-row groups, descriptor version 1, layout type 2 (128B swizzle).
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-
-// mixed-precision FMA: exact 16-bit x 16-bit product added into fp32 (SASS FHFMA / FHFMA.BF16)
-template <typename T> struct MixFma;
-template <> struct MixFma<__half> {
-    __device__ __forceinline__ static void fma2(float& lo, float& hi, uint32_t a, uint32_t b) {
-        asm("{\n\t.reg .f16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %2;\n\tmov.b32 {bl, bh}, %3;\n\t"
-            "fma.rn.f32.f16 %0, al, bl, %0;\n\tfma.rn.f32.f16 %1, ah, bh, %1;\n\t}" : "+f"(lo), "+f"(hi) : "r"(a), "r"(b));
-    }
-    __device__ __forceinline__ static uint32_t pack(float lo, float hi) {
-        __half2 h = __floats2half2_rn(lo, hi);
-        return *reinterpret_cast<uint32_t*>(&h);
-    }
-    __device__ __forceinline__ static float2 unpack(uint32_t v) { return __half22float2(*reinterpret_cast<__half2*>(&v)); }
-    static constexpr uint32_t kUmmaFormat = 0;   // F16
-};
-template <> struct MixFma<__nv_bfloat16> {
-    __device__ __forceinline__ static void fma2(float& lo, float& hi, uint32_t a, uint32_t b) {
-        asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %2;\n\tmov.b32 {bl, bh}, %3;\n\t"
-            "fma.rn.f32.bf16 %0, al, bl, %0;\n\tfma.rn.f32.bf16 %1, ah, bh, %1;\n\t}" : "+f"(lo), "+f"(hi) : "r"(a), "r"(b));
-    }
-    __device__ __forceinline__ static uint32_t pack(float lo, float hi) {
-        __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-        return *reinterpret_cast<uint32_t*>(&h);
-    }
-    __device__ __forceinline__ static float2 unpack(uint32_t v) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v)); }
-    static constexpr uint32_t kUmmaFormat = 1;   // BF16
+    unsigned long long* trace;   // debug timeline (fd_plan_trace_step) or nullptr: [8 rows][TC_TRACE_N] SM clocks of CTA 0
 };
 
 // shared-memory bookkeeping block (after the operand stages)
@@ -218,20 +91,30 @@ struct TcBarriers {
 struct ItemCoord { int img0, oy0, ox0, n0; };
 __device__ __forceinline__ ItemCoord decode_item(const TcParams& p, int w, int NI, int TH, int TW) {
     ItemCoord c;
-    const int split = w % p.splits;
-    int t = w / p.splits;
-    const int tile_x = t % p.tiles_x; t /= p.tiles_x;
-    const int tile_y = t % p.tiles_y; t /= p.tiles_y;
-    c.img0 = t * NI; c.oy0 = tile_y * TH; c.ox0 = tile_x * TW; c.n0 = split * p.n_cta;
+    uint32_t t = fdiv40((uint32_t)w, p.mg_splits);
+    const int split = w - (int)t * p.splits;
+    uint32_t t2 = fdiv40(t, p.mg_tx);
+    const int tile_x = (int)(t - t2 * (uint32_t)p.tiles_x);
+    uint32_t t3 = fdiv40(t2, p.mg_ty);
+    const int tile_y = (int)(t2 - t3 * (uint32_t)p.tiles_y);
+    c.img0 = (int)t3 * NI; c.oy0 = tile_y * TH; c.ox0 = tile_x * TW; c.n0 = split * p.n_cta;
     return c;
 }
 
 // ----------------------------------------------------------------------------------------------
 // the kernel
 // ----------------------------------------------------------------------------------------------
-template <typename T, int KS, int STRIDE, int NI, int TH, int TW>
+// debug timeline: row r, slot i <- SM clock (only CTA 0, only when p.trace != nullptr)
+#define TC_TRACE(row, idx)                                                                       \
+    do {                                                                                         \
+        if (p.trace != nullptr && blockIdx.x == 0 && (idx) < TC_TRACE_N) p.trace[(row) * TC_TRACE_N + (idx)] = clock64(); \
+    } while (0)
+
+template <typename T, int KS, int STRIDE, int NI, int TH, int TW, bool RELU6>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w, const TcParams p) {
+block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w,
+                const __grid_constant__ CUtensorMap tm_o0, const __grid_constant__ CUtensorMap tm_o1,
+                const __grid_constant__ CUtensorMap tm_o2, const __grid_constant__ CUtensorMap tm_o3, const TcParams p) {
     static_assert(NI * TH * TW == 128, "tile must hold 128 pixels");
     static_assert(NI * (TH / 4) * (TW / 4) == TC_DW_WARPS, "one 4x4 pixel block per depthwise warp");
     constexpr int PAD = (KS - 1) / 2;
@@ -242,16 +125,16 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
-    // carve-up: [A stages][B stages][input stages (+ dw parameter block each)][pw BN vectors][barriers]
+    // carve-up: [A stages][B stages][input stages (+ dw parameter block each)][epilogue staging][pw BN vectors][barriers]
     const uint32_t a_off = 0;
     const uint32_t b_off = a_off + p.s_a * TC_A_STAGE_BYTES;
     const uint32_t in_off = b_off + p.s_b * p.b_stage_bytes;
-    const uint32_t pw_off = in_off + p.s_in * p.in_stage_stride;
+    const uint32_t stg_off = (in_off + p.s_in * p.in_stage_stride + 1023u) & ~1023u;   // epilogue staging: [128 px][64 ch] 16-bit, SW128 atoms
+    const uint32_t pw_off = stg_off + (uint32_t)p.n_stg * 16384u;
     const uint32_t bar_off = pw_off + 3u * (uint32_t)p.cpad_all * 4u;
     TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem + bar_off);
-    float* s_pw_scale = reinterpret_cast<float*>(smem + pw_off);
-    float* s_pw_bias = s_pw_scale + p.cpad_all;
-    float* s_head_w = s_pw_bias + p.cpad_all;
+    float2* s_pw_affine = reinterpret_cast<float2*>(smem + pw_off);           // (scale, bias) per output channel
+    float* s_head_w = reinterpret_cast<float*>(s_pw_affine + p.cpad_all);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -266,10 +149,10 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
     if (warp == TC_WARP_TMA && lane == 0) {
         tma_prefetch_desc(&tm_in);
         tma_prefetch_desc(&tm_w);
+        if (p.epi_tma) { tma_prefetch_desc(&tm_o0); if (p.upsample) { tma_prefetch_desc(&tm_o1); tma_prefetch_desc(&tm_o2); tma_prefetch_desc(&tm_o3); } }
     }
     for (int i = threadIdx.x; i < p.cpad_all; i += TC_THREADS) {          // pointwise BN affine (+ head weights) -> smem
-        s_pw_scale[i] = p.pw_scale[i];
-        s_pw_bias[i] = p.pw_bias[i];
+        s_pw_affine[i] = p.pw_affine[i];
         s_head_w[i] = p.head ? p.head_w[i] : 0.f;
     }
     tc_fence_before();
@@ -280,12 +163,13 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
     if (warp == TC_WARP_TMA) {
         // =========================== TMA producer ===========================
         if (lane == 0) {
-            uint32_t it = 0, jb = 0;
+            Ring rin, rb;
+            int tr = 0;
             bool first = true;
             for (int w = blockIdx.x; w < p.items; w += gridDim.x, first = false) {
                 const ItemCoord c = decode_item(p, w, NI, TH, TW);
-                for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
-                    const uint32_t s = it % (uint32_t)p.s_in, ph = (it / (uint32_t)p.s_in) & 1u;
+                for (int kb = 0; kb < p.kblocks; ++kb, rin.next((uint32_t)p.s_in)) {
+                    const uint32_t s = rin.s, ph = rin.ph;
                     mbar_wait(smem_u32(&bars->in_empty[s]), ph ^ 1u);
                     mbar_expect_tx(smem_u32(&bars->in_full[s]), (uint32_t)(p.in_stage_bytes + p.dwp_bytes));
                     tma_load_4d(smem_base + in_off + s * p.in_stage_stride, &tm_in, smem_u32(&bars->in_full[s]), kb * TC_KBLK,
@@ -293,14 +177,16 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                     bulk_load(smem_base + in_off + s * p.in_stage_stride + p.in_stage_bytes,
                               reinterpret_cast<const uint8_t*>(p.dwp) + (size_t)kb * p.dwp_bytes, (uint32_t)p.dwp_bytes,
                               smem_u32(&bars->in_full[s]));
+                    TC_TRACE(0, tr); ++tr;
                     if (p.b_resident && !first) continue;
-                    for (int nbi = 0; nbi < p.nb; ++nbi, ++jb) {
+                    for (int nbi = 0; nbi < p.nb; ++nbi) {
                         uint32_t sb;
                         if (p.b_resident) {
                             sb = (uint32_t)(kb * p.nb + nbi);
                         } else {
-                            sb = jb % (uint32_t)p.s_b;
-                            mbar_wait(smem_u32(&bars->b_empty[sb]), ((jb / (uint32_t)p.s_b) & 1u) ^ 1u);
+                            sb = rb.s;
+                            mbar_wait(smem_u32(&bars->b_empty[sb]), rb.ph ^ 1u);
+                            rb.next((uint32_t)p.s_b);
                         }
                         mbar_expect_tx(smem_u32(&bars->b_full[sb]), (uint32_t)p.b_stage_bytes);
                         tma_load_2d(smem_base + b_off + sb * p.b_stage_bytes, &tm_w, smem_u32(&bars->b_full[sb]), kb * TC_KBLK,
@@ -311,41 +197,52 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         }
     } else if (warp == TC_WARP_MMA) {
         // =========================== MMA issuer ===========================
+        // A single thread drives the tensor core; every instruction on this path is serial latency for the whole
+        // CTA, so descriptors are pre-split (constant high word) and advanced with 32-bit adds only.
         if (lane == 0) {
-            // instruction descriptor: D fp32, A/B 16-bit K-major, M = 128, N filled per sub-block
             const uint32_t idesc_base = (1u << 4) | (MF::kUmmaFormat << 7) | (MF::kUmmaFormat << 10) | ((128u >> 4) << 24);
-            uint32_t it = 0, jb = 0, i = 0;
-            for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++i) {
-                const uint32_t ab = i % (uint32_t)p.nacc, pa = (i / (uint32_t)p.nacc) & 1u;
-                mbar_wait(smem_u32(&bars->acc_empty[ab]), pa ^ 1u);          // epilogue has drained this accumulator
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + ab * (uint32_t)p.n_cta;
-                for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
-                    const uint32_t sa = it % (uint32_t)p.s_a, pha = (it / (uint32_t)p.s_a) & 1u;
-                    mbar_wait(smem_u32(&bars->a_full[sa]), pha);
+            const uint32_t idesc_full = idesc_base | ((uint32_t)(p.bn >> 3) << 17);
+            const uint32_t idesc_last = idesc_base | ((uint32_t)((p.n_cta - (p.nb - 1) * p.bn) >> 3) << 17);
+            const uint32_t a_lo0 = sw128_desc_lo(smem_base + a_off), b_lo0 = sw128_desc_lo(smem_base + b_off);
+            const uint32_t a_step = TC_A_STAGE_BYTES >> 4, b_step = (uint32_t)p.b_stage_bytes >> 4;
+            const uint32_t bar_a_full = smem_u32(&bars->a_full[0]), bar_a_empty = smem_u32(&bars->a_empty[0]);
+            const uint32_t bar_b_full = smem_u32(&bars->b_full[0]), bar_b_empty = smem_u32(&bars->b_empty[0]);
+            const uint32_t bar_acc_full = smem_u32(&bars->acc_full[0]), bar_acc_empty = smem_u32(&bars->acc_empty[0]);
+            Ring ra, rb, racc;
+            int tr = 0;
+            bool first = true;
+            for (int w = blockIdx.x; w < p.items; w += gridDim.x, racc.next((uint32_t)p.nacc), first = false) {
+                mbar_wait(bar_acc_empty + 8u * racc.s, racc.ph ^ 1u);          // epilogue has drained this accumulator
+                const uint32_t d_tmem = tmem_base + racc.s * (uint32_t)p.n_cta;
+                for (int kb = 0; kb < p.kblocks; ++kb, ra.next((uint32_t)p.s_a)) {
+                    mbar_wait(bar_a_full + 8u * ra.s, ra.ph);
                     tc_fence_after();
-                    const uint64_t a_desc = make_kmajor_sw128_desc(smem_base + a_off + sa * TC_A_STAGE_BYTES);
-                    for (int nbi = 0; nbi < p.nb; ++nbi, ++jb) {
+                    TC_TRACE(4, tr);
+                    const uint32_t a_lo = a_lo0 + ra.s * a_step;
+                    for (int nbi = 0; nbi < p.nb; ++nbi) {
                         uint32_t sb;
                         if (p.b_resident) {
                             sb = (uint32_t)(kb * p.nb + nbi);
-                            if (i == 0) { mbar_wait(smem_u32(&bars->b_full[sb]), 0); tc_fence_after(); }
+                            if (first) { mbar_wait(bar_b_full + 8u * sb, 0); tc_fence_after(); }
                         } else {
-                            sb = jb % (uint32_t)p.s_b;
-                            mbar_wait(smem_u32(&bars->b_full[sb]), (jb / (uint32_t)p.s_b) & 1u);
+                            sb = rb.s;
+                            mbar_wait(bar_b_full + 8u * sb, rb.ph);
+                            rb.next((uint32_t)p.s_b);
                             tc_fence_after();
                         }
-                        const uint64_t b_desc = make_kmajor_sw128_desc(smem_base + b_off + sb * p.b_stage_bytes);
-                        const int n_cur = min(p.bn, p.n_cta - nbi * p.bn);
-                        const uint32_t idesc = idesc_base | ((uint32_t)(n_cur >> 3) << 17);
-#pragma unroll
-                        for (int k = 0; k < TC_KBLK / 16; ++k)     // advance 32 B (16 elements) inside the swizzle row
-                            umma_f16(d_tmem + nbi * p.bn, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                        if (!p.b_resident) umma_commit(smem_u32(&bars->b_empty[sb]));
+                        const uint32_t b_lo = b_lo0 + sb * b_step;
+                        const uint32_t idesc = (nbi == p.nb - 1) ? idesc_last : idesc_full;
+                        const uint32_t dcol = d_tmem + (uint32_t)(nbi * p.bn);
+                        umma_f16_lohi(dcol, a_lo, b_lo, kSw128DescHi, idesc, kb > 0 ? 1u : 0u);
+                        umma_f16_lohi(dcol, a_lo + 2, b_lo + 2, kSw128DescHi, idesc, 1u);     // +32 B (16 elements) per K step
+                        umma_f16_lohi(dcol, a_lo + 4, b_lo + 4, kSw128DescHi, idesc, 1u);
+                        umma_f16_lohi(dcol, a_lo + 6, b_lo + 6, kSw128DescHi, idesc, 1u);
+                        if (!p.b_resident) umma_commit(bar_b_empty + 8u * sb);
                     }
-                    umma_commit(smem_u32(&bars->a_empty[sa]));
+                    umma_commit(bar_a_empty + 8u * ra.s);
+                    TC_TRACE(5, tr); ++tr;
                 }
-                umma_commit(smem_u32(&bars->acc_full[ab]));
+                umma_commit(bar_acc_full + 8u * racc.s);
             }
         }
     } else if (warp < TC_DW_WARPS) {
@@ -354,12 +251,14 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         const int ni = warp / BPI, rem = warp % BPI;
         const int br = rem / BPR, bc = rem % BPR;
         const uint32_t in_warp_off = (uint32_t)((ni * IH + br * 4 * STRIDE) * IW + bc * 4 * STRIDE) * 128u + lane * 4u;
-        uint32_t it = 0;
+        Ring rin, ra;
+        int tr = 0;
+        const bool tracer = warp == 0 && lane == 0;
         for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
-            for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
-                const uint32_t s = it % (uint32_t)p.s_in, ph = (it / (uint32_t)p.s_in) & 1u;
-                const uint32_t sa = it % (uint32_t)p.s_a, pha = (it / (uint32_t)p.s_a) & 1u;
+            for (int kb = 0; kb < p.kblocks; ++kb, rin.next((uint32_t)p.s_in), ra.next((uint32_t)p.s_a)) {
+                const uint32_t s = rin.s, ph = rin.ph, sa = ra.s, pha = ra.ph;
                 mbar_wait(smem_u32(&bars->in_full[s]), ph);
+                if (tracer) TC_TRACE(1, tr);
                 const uint8_t* stage = smem + in_off + s * p.in_stage_stride;
                 const uint8_t* in_s = stage + in_warp_off;
                 // this K-block's depthwise taps + folded BN for the lane's channel pair (landed with the tile)
@@ -394,6 +293,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bars->in_empty[s]));
 
+                if (tracer) TC_TRACE(2, tr);
                 mbar_wait(smem_u32(&bars->a_empty[sa]), pha ^ 1u);
                 uint8_t* a_s = smem + a_off + sa * TC_A_STAGE_BYTES;
 #pragma unroll
@@ -401,13 +301,14 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
 #pragma unroll
                     for (int ox = 0; ox < 4; ++ox) {
                         const int m = (ni * TH + br * 4 + oy) * TW + bc * 4 + ox;
-                        const float lo = apply_act(fmaf(acc[oy][ox][0], sc.x, bi.x), p.act);
-                        const float hi = apply_act(fmaf(acc[oy][ox][1], sc.y, bi.y), p.act);
+                        const float lo = affine_act<RELU6>(acc[oy][ox][0], sc.x, bi.x);
+                        const float hi = affine_act<RELU6>(acc[oy][ox][1], sc.y, bi.y);
                         *reinterpret_cast<uint32_t*>(a_s + m * 128 + (((lane >> 2) ^ (m & 7)) << 4) + ((lane & 3) << 2)) = MF::pack(lo, hi);
                     }
                 fence_proxy_async();             // generic-proxy writes -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bars->a_full[sa]));
+                if (tracer) { TC_TRACE(3, tr); ++tr; }
             }
         }
     } else {
@@ -419,75 +320,127 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         const int batches = (p.n_cta + 31) >> 5;           // 32 accumulator columns per batch
         T* __restrict__ outp = reinterpret_cast<T*>(p.out);
         const T* __restrict__ skipp = reinterpret_cast<const T*>(p.skip);
-        uint32_t i = 0;
-        for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++i) {
+        Ring racc;
+        int tr = 0;
+        uint32_t stg_flip = 0;
+        for (int w = blockIdx.x; w < p.items; w += gridDim.x, racc.next((uint32_t)p.nacc)) {
             const ItemCoord c = decode_item(p, w, NI, TH, TW);
-            const uint32_t ab = i % (uint32_t)p.nacc, pa = (i / (uint32_t)p.nacc) & 1u;
+            const uint32_t ab = racc.s, pa = racc.ph;
             const int img = c.img0 + e_ni, oy = c.oy0 + e_ty, ox = c.ox0 + e_tx;
             const bool valid = img < p.n && oy < p.h_out && ox < p.w_out;
             mbar_wait(smem_u32(&bars->acc_full[ab]), pa);
             tc_fence_after();
+            if (ew == 0 && lane == 0) TC_TRACE(6, tr);
             const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + ab * (uint32_t)p.n_cta;
 
             if (!p.head) {
-                for (int b = hsel; b < batches; b += 2) {
-                    uint32_t r[32];
-                    const bool full = b * 32 + 32 <= p.n_cta;          // n_cta is a multiple of 16
-                    if (full) tmem_ld32_sync(t_lane + b * 32, r);
-                    else tmem_ld16_sync(t_lane + b * 32, r);
-#pragma unroll
-                    for (int hg = 0; hg < 2; ++hg) {                   // two 16-column groups
-                        if (hg == 1 && !full) break;
-                        const int c0 = c.n0 + b * 32 + hg * 16;
-                        uint32_t pk[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float2 s2 = *reinterpret_cast<const float2*>(s_pw_scale + c0 + 2 * j);
-                            const float2 b2 = *reinterpret_cast<const float2*>(s_pw_bias + c0 + 2 * j);
-                            const float lo = apply_act(fmaf(__uint_as_float(r[hg * 16 + 2 * j]), s2.x, b2.x), p.act);
-                            const float hi = apply_act(fmaf(__uint_as_float(r[hg * 16 + 2 * j + 1]), s2.y, b2.y), p.act);
-                            pk[j] = MF::pack(lo, hi);
+                // Two phases per block of 64 output channels so that global memory sees whole 128-byte lines:
+                //  A: TMEM -> BN affine + act -> 16-bit -> shared staging tile [128 pixels][64 ch] (16-byte chunks XOR-swizzled)
+                //  B: 8 consecutive lanes move one pixel's 128 contiguous bytes (x4 positions + skip for decoder blocks)
+                const int nblk = (p.n_cta + 63) >> 6;
+                for (int cb = 0; cb < nblk; ++cb) {
+                    uint8_t* stg = smem + stg_off + (p.n_stg == 2 ? (stg_flip & 1u) * 16384u : 0u);
+                    ++stg_flip;
+                    if (p.n_stg == 1 && (cb > 0 || stg_flip > 1)) {      // single staging buffer: wait until it is free again
+                        if (p.epi_tma && ew == 0 && lane == 0) bulk_wait_read0();
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                    }
+                    const int col0 = cb * 64 + hsel * 32;                 // first accumulator column of this warp
+                    if (col0 < p.n_cta) {
+                        uint32_t r[32];
+                        const bool full = col0 + 32 <= p.n_cta;           // n_cta is a multiple of 16
+                        if (full) tmem_ld32_sync(t_lane + col0, r);
+                        else tmem_ld16_sync(t_lane + col0, r);
+                        if (cb == nblk - 1) {                             // last TMEM read of this item: release the accumulator early
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));
                         }
-                        // stores are predicated (no divergent early-out: the next tcgen05.ld is warp-collective)
-                        const bool v0 = valid && c0 + 8 <= p.c_out, v1 = valid && c0 + 16 <= p.c_out;
+                        uint8_t* row = stg + m * 128;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {                     // 8 channels -> one 16-byte chunk
+                            if (g >= 2 && !full) break;
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 af = *reinterpret_cast<const float4*>(s_pw_affine + c.n0 + col0 + g * 8 + 2 * j);   // s0, b0, s1, b1
+                                pk[j] = MF::pack(affine_act<RELU6>(__uint_as_float(r[g * 8 + 2 * j]), af.x, af.y),
+                                                 affine_act<RELU6>(__uint_as_float(r[g * 8 + 2 * j + 1]), af.z, af.w));
+                            }
+                            *reinterpret_cast<uint4*>(row + (((hsel * 4 + g) ^ (m & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
+                    } else if (cb == nblk - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));
+                    }
+                    if (p.epi_tma) {
+                        // the tile leaves through the TMA: one elected thread, asynchronous, whole 128-byte lines, image
+                        // borders and channel tails clipped by the hardware.  Before anyone may overwrite the other
+                        // staging buffer its previous store must have finished READING shared memory.
+                        fence_proxy_async();
+                        if (ew == 0 && lane == 0) bulk_wait_read0();
+                        asm volatile("bar.sync 1, 256;" ::: "memory");    // staging tile complete + other buffer free
+                        if (ew == 0 && lane == 0) {
+                            const uint32_t src = smem_u32(stg);
+                            const int cc = c.n0 + cb * 64;
+                            if (!p.upsample) {
+                                tma_store_4d(&tm_o0, src, cc, c.ox0, c.oy0, c.img0);
+                            } else if (!p.epi_red) {
+                                tma_store_4d(&tm_o0, src, cc, c.ox0, c.oy0, c.img0);
+                                tma_store_4d(&tm_o1, src, cc, c.ox0, c.oy0, c.img0);
+                                tma_store_4d(&tm_o2, src, cc, c.ox0, c.oy0, c.img0);
+                                tma_store_4d(&tm_o3, src, cc, c.ox0, c.oy0, c.img0);
+                            } else {
+                                tma_reduce_add_4d(&tm_o0, src, cc, c.ox0, c.oy0, c.img0);
+                                tma_reduce_add_4d(&tm_o1, src, cc, c.ox0, c.oy0, c.img0);
+                                tma_reduce_add_4d(&tm_o2, src, cc, c.ox0, c.oy0, c.img0);
+                                tma_reduce_add_4d(&tm_o3, src, cc, c.ox0, c.oy0, c.img0);
+                            }
+                            bulk_commit_group();
+                        }
+                        continue;
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");        // staging tile complete
+                    const int et = ew * 32 + lane;                        // 0..255 over the 8 epilogue warps
+                    const int ch = et & 7;                                // 16-byte chunk within the 64-channel block
+                    const int ccol = cb * 64 + ch * 8;                    // accumulator column of that chunk
+                    const bool cok = ccol < p.n_cta && c.n0 + ccol + 8 <= p.c_out;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int rr = (et >> 3) + 32 * k;                // pixel row of the tile
+                        const int r_ni = rr / (TH * TW), r_ty = (rr / TW) % TH, r_tx = rr % TW;
+                        const int img = c.img0 + r_ni, oy = c.oy0 + r_ty, ox = c.ox0 + r_tx;
+                        if (!(cok && img < p.n && oy < p.h_out && ox < p.w_out)) continue;
+                        const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
                         if (!p.upsample) {
-                            T* o = outp + (((size_t)img * p.h_out + oy) * p.w_out + ox) * p.c_out + c0;
-                            if (v0) *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                            if (v1) *reinterpret_cast<uint4*>(o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                            *reinterpret_cast<uint4*>(outp + (((size_t)img * p.h_out + oy) * p.w_out + ox) * p.c_out + c.n0 + ccol) = v;
                         } else {
                             const int w2 = 2 * p.w_out;
-                            const size_t off00 = (((size_t)img * 2 * p.h_out + 2 * oy) * w2 + 2 * ox) * p.c_out + c0;
+                            const size_t off00 = (((size_t)img * 2 * p.h_out + 2 * oy) * w2 + 2 * ox) * p.c_out + c.n0 + ccol;
                             size_t off[4];
 #pragma unroll
                             for (int d = 0; d < 4; ++d) off[d] = off00 + ((size_t)(d >> 1) * w2 + (d & 1)) * p.c_out;
                             if (skipp != nullptr) {
-                                // x = interpolate(x) (already rounded to the storage dtype); x = x + skip (models.py:723-729).
-                                // all eight skip vectors are requested before the first is consumed
-                                uint4 sv[4][2];
+                                // x = interpolate(x) (already rounded to the storage dtype); x = x + skip (models.py:723-729)
+                                uint4 sv[4];
+#pragma unroll
+                                for (int d = 0; d < 4; ++d) sv[d] = __ldg(reinterpret_cast<const uint4*>(skipp + off[d]));
+                                const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                                 for (int d = 0; d < 4; ++d) {
-                                    sv[d][0] = v0 ? __ldg(reinterpret_cast<const uint4*>(skipp + off[d])) : make_uint4(0, 0, 0, 0);
-                                    sv[d][1] = v1 ? __ldg(reinterpret_cast<const uint4*>(skipp + off[d] + 8)) : make_uint4(0, 0, 0, 0);
-                                }
+                                    const uint32_t sk[4] = {sv[d].x, sv[d].y, sv[d].z, sv[d].w};
+                                    uint32_t z[4];
 #pragma unroll
-                                for (int d = 0; d < 4; ++d) {
-                                    const uint32_t sk[8] = {sv[d][0].x, sv[d][0].y, sv[d][0].z, sv[d][0].w,
-                                                            sv[d][1].x, sv[d][1].y, sv[d][1].z, sv[d][1].w};
-                                    uint32_t z[8];
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) {
-                                        const float2 a = MF::unpack(pk[j]), bq = MF::unpack(sk[j]);
+                                    for (int j = 0; j < 4; ++j) {
+                                        const float2 a = MF::unpack(vv[j]), bq = MF::unpack(sk[j]);
                                         z[j] = MF::pack(a.x + bq.x, a.y + bq.y);
                                     }
-                                    if (v0) *reinterpret_cast<uint4*>(outp + off[d]) = make_uint4(z[0], z[1], z[2], z[3]);
-                                    if (v1) *reinterpret_cast<uint4*>(outp + off[d] + 8) = make_uint4(z[4], z[5], z[6], z[7]);
+                                    *reinterpret_cast<uint4*>(outp + off[d]) = make_uint4(z[0], z[1], z[2], z[3]);
                                 }
                             } else {
 #pragma unroll
-                                for (int d = 0; d < 4; ++d) {
-                                    if (v0) *reinterpret_cast<uint4*>(outp + off[d]) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                                    if (v1) *reinterpret_cast<uint4*>(outp + off[d] + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                                }
+                                for (int d = 0; d < 4; ++d) *reinterpret_cast<uint4*>(outp + off[d]) = v;
                             }
                         }
                     }
@@ -504,11 +457,10 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                     for (int j = 0; j < 16; ++j) {
                         if (j >= 8 && !full) break;
                         const int c0 = b * 32 + 2 * j;
-                        const float2 s2 = *reinterpret_cast<const float2*>(s_pw_scale + c0);
-                        const float2 b2 = *reinterpret_cast<const float2*>(s_pw_bias + c0);
+                        const float4 af = *reinterpret_cast<const float4*>(s_pw_affine + c0);
                         const float2 hw = *reinterpret_cast<const float2*>(s_head_w + c0);
-                        const float lo = apply_act(fmaf(__uint_as_float(r[2 * j]), s2.x, b2.x), p.act);
-                        const float hi = apply_act(fmaf(__uint_as_float(r[2 * j + 1]), s2.y, b2.y), p.act);
+                        const float lo = affine_act<RELU6>(__uint_as_float(r[2 * j]), af.x, af.y);
+                        const float hi = affine_act<RELU6>(__uint_as_float(r[2 * j + 1]), af.z, af.w);
                         const float2 rq = MF::unpack(MF::pack(lo, hi));      // decode_conv5's output is stored in 16 bits
                         dot = fmaf(rq.x, hw.x, dot);
                         dot = fmaf(rq.y, hw.y, dot);
@@ -522,11 +474,14 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                     *reinterpret_cast<uint32_t*>(ho + 2 * p.w_out) = yy;
                 }
             }
-            // accumulator drained: hand the TMEM buffer back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));
+            if (p.head) {                                            // (the non-head path released it after its last TMEM read)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));
+            }
+            if (ew == 0 && lane == 0) { TC_TRACE(7, tr); ++tr; }
         }
+        if (p.epi_tma && ew == 0 && lane == 0) bulk_wait_all();      // all tensor stores of this CTA have landed
     }
 
     tc_fence_before();
@@ -540,11 +495,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
 // ----------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode() {
+PFN_encodeTiled get_tensor_map_encoder() {
     static PFN_encodeTiled fn = nullptr;
     if (fn) return fn;
     void* ptr = nullptr;
@@ -553,16 +504,16 @@ static PFN_encodeTiled get_encode() {
     fn = reinterpret_cast<PFN_encodeTiled>(ptr);
     return fn;
 }
+static PFN_encodeTiled get_encode() { return get_tensor_map_encoder(); }
 
 struct BlockTcPlan {
-    CUtensorMap tm_in, tm_w;
+    CUtensorMap tm_in, tm_w, tm_o[4];
     TcParams p;
     dim3 grid;
     size_t smem_bytes;
     int dtype, ks, stride, tile;           // tile: 0 = (1,8,16), 1 = (2,8,8)
     void* dwp = nullptr;                   // owned device copies (packed / padded)
-    float* pw_scale = nullptr;
-    float* pw_bias = nullptr;
+    float2* pw_affine = nullptr;
     float* head_w = nullptr;
     std::string name;
 };
@@ -580,17 +531,22 @@ bool block_tc_supported(int dtype, const StageGeom& g, bool head_fused) {
     return get_encode() != nullptr;
 }
 
-template <typename T, int KS, int STRIDE, int NI, int TH, int TW>
-static int launch_inst(BlockTcPlan* bp, cudaStream_t st) {
-    auto kern = block_tc_kernel<T, KS, STRIDE, NI, TH, TW>;
+template <typename T, int KS, int STRIDE, int NI, int TH, int TW, bool RELU6>
+static int launch_inst2(BlockTcPlan* bp, cudaStream_t st) {
+    auto kern = block_tc_kernel<T, KS, STRIDE, NI, TH, TW, RELU6>;
     static bool attr_set = false;
     if (!attr_set) {
         FD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    kern<<<bp->grid, TC_THREADS, bp->smem_bytes, st>>>(bp->tm_in, bp->tm_w, bp->p);
+    kern<<<bp->grid, TC_THREADS, bp->smem_bytes, st>>>(bp->tm_in, bp->tm_w, bp->tm_o[0], bp->tm_o[1], bp->tm_o[2], bp->tm_o[3], bp->p);
     FD_CUDA_OK(cudaGetLastError());
     return FD_OK;
+}
+template <typename T, int KS, int STRIDE, int NI, int TH, int TW>
+static int launch_inst(BlockTcPlan* bp, cudaStream_t st) {
+    return bp->p.act == FD_ACT_RELU6 ? launch_inst2<T, KS, STRIDE, NI, TH, TW, true>(bp, st)
+                                     : launch_inst2<T, KS, STRIDE, NI, TH, TW, false>(bp, st);
 }
 
 template <typename T>
@@ -617,25 +573,45 @@ int block_tc_launch(BlockTcPlan* bp, cudaStream_t st, void* head_out) {
 
 const char* block_tc_name(BlockTcPlan* bp) { return bp->name.c_str(); }
 
+// debug: run once with the timeline enabled; out_host[8 * TC_TRACE_N] SM clocks of CTA 0 (0 = slot unused)
+int block_tc_trace(BlockTcPlan* bp, cudaStream_t st, void* head_out, unsigned long long* out_host, int* rows, int* cols) {
+    unsigned long long* dev = nullptr;
+    const size_t bytes = 8 * TC_TRACE_N * sizeof(unsigned long long);
+    FD_CUDA_OK(cudaMalloc(&dev, bytes));
+    FD_CUDA_OK(cudaMemsetAsync(dev, 0, bytes, st));
+    bp->p.trace = dev;
+    int rc = block_tc_launch(bp, st, head_out);
+    bp->p.trace = nullptr;
+    if (rc == FD_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(FD_ERR_CUDA, "trace run failed");
+    if (rc == FD_OK) cudaMemcpy(out_host, dev, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(dev);
+    *rows = 8; *cols = TC_TRACE_N;
+    return rc;
+}
+
 void block_tc_destroy(BlockTcPlan* bp) {
     if (!bp) return;
-    cudaFree(bp->dwp); cudaFree(bp->pw_scale); cudaFree(bp->pw_bias);
-    cudaFree(bp->head_w);
+    cudaFree(bp->dwp); cudaFree(bp->pw_affine); cudaFree(bp->head_w);
     delete bp;
 }
 
 // per-K-block depthwise parameter block: [taps][64] 16-bit taps | [64] fp32 scale | [64] fp32 bias (zero padded)
 template <typename T>
 __global__ void pack_dwp_kernel(const float* __restrict__ w, const float* __restrict__ scale, const float* __restrict__ bias,
-                                uint8_t* __restrict__ dst, int taps, int c_in, int kblocks, int block_bytes) {
+                                uint8_t* __restrict__ dst, int taps, int c_in, int kblocks, int block_bytes, float post) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= kblocks * 64) return;
     const int kb = i / 64, cl = i % 64, c = kb * 64 + cl;
     uint8_t* blk = dst + (size_t)kb * block_bytes;
     T* wt = reinterpret_cast<T*>(blk);
     for (int t = 0; t < taps; ++t) wt[t * 64 + cl] = Traits<T>::from_f(c < c_in ? w[t * c_in + c] : 0.f);
-    reinterpret_cast<float*>(blk + taps * 128)[cl] = c < c_in ? scale[c] : 0.f;
-    reinterpret_cast<float*>(blk + taps * 128 + 256)[cl] = c < c_in ? bias[c] : 0.f;
+    reinterpret_cast<float*>(blk + taps * 128)[cl] = c < c_in ? scale[c] * post : 0.f;
+    reinterpret_cast<float*>(blk + taps * 128 + 256)[cl] = c < c_in ? bias[c] * post : 0.f;
+}
+__global__ void pack_affine_kernel(const float* __restrict__ scale, const float* __restrict__ bias, float2* __restrict__ dst,
+                                   int n_src, int n_dst, float post) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_dst) dst[i] = i < n_src ? make_float2(scale[i] * post, bias[i] * post) : make_float2(0.f, 0.f);
 }
 __global__ void pad_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_src, int n_dst) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -650,7 +626,7 @@ static int padded_copy(const float* src, int n_src, int n_dst, float** out) {
 }
 
 int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float head_scale, float head_bias, int head_act,
-                     void* head_out, BlockTcPlan** out) {
+                     void* head_out, bool tma_epilogue, BlockTcPlan** out) {
     PFN_encodeTiled encode = get_encode();
     if (!encode) return fail(FD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     const StageGeom& g = a.g;
@@ -676,6 +652,9 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
     int splits = 1;
     while ((cout_pad + splits - 1) / splits > 256 || (n_tiles * splits < 148 && (cout_pad / (splits * 2)) >= 64 && !p.head)) splits *= 2;
     p.n_cta = ((cout_pad + splits - 1) / splits + 15) / 16 * 16;
+    // with several splits every item's channel range must end on a 64-channel boundary: the epilogue moves whole
+    // [128 px][64 ch] tiles and must not touch a neighbouring split's columns
+    if (splits > 1) p.n_cta = (p.n_cta + 63) / 64 * 64;
     splits = (cout_pad + p.n_cta - 1) / p.n_cta;
     p.splits = splits;
     p.items = n_tiles * splits;
@@ -687,46 +666,60 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
     p.dwp_bytes = taps * 128 + 512;
     p.in_stage_stride = (p.in_stage_bytes + p.dwp_bytes + 127) / 128 * 128;
     p.cpad_all = p.n_cta * splits;
-    p.s_a = 2;
-    const int avail = 212 * 1024 - (int)sizeof(TcBarriers) - 1024 - p.s_a * TC_A_STAGE_BYTES - 3 * p.cpad_all * 4;
-    // weights: resident when the whole [cin_pad x n_cta] matrix is small and every item uses the same one
-    p.bn = p.n_cta < 256 ? p.n_cta : 256;
-    p.nb = (p.n_cta + p.bn - 1) / p.bn;
-    const int w_all = p.kblocks * p.nb * p.bn * 128;
-    p.b_resident = (splits == 1 && p.kblocks * p.nb <= TC_MAX_B && w_all <= 64 * 1024 && w_all + 2 * p.in_stage_stride <= avail) ? 1 : 0;
-    if (p.b_resident) {
-        p.s_b = p.kblocks * p.nb;
-    } else {
-        p.s_b = 2;
-        while (p.bn > 16 && p.s_b * p.bn * 128 + 2 * p.in_stage_stride > avail) p.bn = (p.bn / 2 + 15) / 16 * 16;
+    // shared-memory plan: try the deepest A ring / double staging first, fall back when the input stages are large
+    // (stride-2 blocks stage 72 KB per K-block).  A deep A ring hides the serial latency of the MMA issue thread.
+    bool fits = false;
+    for (int attempt = 0; attempt < 4 && !fits; ++attempt) {
+        p.s_a = attempt == 0 ? 4 : (attempt == 1 ? 3 : 2);
+        p.n_stg = p.head ? 0 : (attempt <= 1 ? 2 : (attempt == 2 ? 2 : 1));
+        const int avail = 212 * 1024 - (int)sizeof(TcBarriers) - 2048 - p.s_a * TC_A_STAGE_BYTES - 3 * p.cpad_all * 4 - p.n_stg * 16384;
+        // weights: resident when the whole [cin_pad x n_cta] matrix is small and every item uses the same one
+        p.bn = p.n_cta < 256 ? p.n_cta : 256;
         p.nb = (p.n_cta + p.bn - 1) / p.bn;
-        while (p.s_b < 4 && (p.s_b + 1) * p.bn * 128 + 2 * p.in_stage_stride <= avail && p.s_b < p.kblocks * p.nb) ++p.s_b;
+        const int w_all = p.kblocks * p.nb * p.bn * 128;
+        p.b_resident = (splits == 1 && p.kblocks * p.nb <= TC_MAX_B && w_all <= 64 * 1024 && w_all + 2 * p.in_stage_stride <= avail) ? 1 : 0;
+        if (p.b_resident) {
+            p.s_b = p.kblocks * p.nb;
+        } else {
+            p.s_b = 2;
+            while (p.bn > 16 && p.s_b * p.bn * 128 + 2 * p.in_stage_stride > avail) p.bn = (p.bn / 2 + 15) / 16 * 16;
+            p.nb = (p.n_cta + p.bn - 1) / p.bn;
+            while (p.s_b < 3 && (p.s_b + 1) * p.bn * 128 + 4 * p.in_stage_stride <= avail && p.s_b < p.kblocks * p.nb) ++p.s_b;
+        }
+        p.b_stage_bytes = p.bn * 128;
+        p.s_in = (avail - p.s_b * p.b_stage_bytes) / p.in_stage_stride;
+        if (p.s_in > TC_MAX_IN) p.s_in = TC_MAX_IN;
+        fits = p.s_in >= 2 && (p.bn >= 64 || p.bn == p.n_cta);
+        if (!fits && attempt == 3) fits = p.s_in >= 1;
     }
-    p.b_stage_bytes = p.bn * 128;
-    p.s_in = (avail - p.s_b * p.b_stage_bytes) / p.in_stage_stride;
-    if (p.s_in > TC_MAX_IN) p.s_in = TC_MAX_IN;
-    if (p.s_in < 1) { delete bp; return fail(FD_ERR_UNSUPPORTED, "fused block does not fit shared memory"); }
+    if (!fits) { delete bp; return fail(FD_ERR_UNSUPPORTED, "fused block does not fit shared memory"); }
     bp->smem_bytes = (size_t)p.s_a * TC_A_STAGE_BYTES + (size_t)p.s_b * p.b_stage_bytes + (size_t)p.s_in * p.in_stage_stride +
-                     3 * (size_t)p.cpad_all * 4 + sizeof(TcBarriers) + 1024;
+                     (size_t)p.n_stg * 16384 + 1024 + 3 * (size_t)p.cpad_all * 4 + sizeof(TcBarriers) + 1024;
     int sms = 148;
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
     bp->grid = dim3((unsigned)(p.items < sms ? p.items : sms), 1, 1);
 
     // packed / padded parameter copies (device -> device)
     int rc = FD_OK;
+    const float post = g.act == FD_ACT_RELU6 ? (1.0f / 6.0f) : 1.0f;    // ReLU6 is evaluated as 6 * sat(acc*s/6 + b/6)
+    auto magic = [](int d) { return (unsigned long long)((1ULL << 40) / (unsigned long long)d) + 1ULL; };
+    p.mg_splits = magic(p.splits); p.mg_tx = magic(p.tiles_x); p.mg_ty = magic(p.tiles_y);
     if (cudaMalloc(&bp->dwp, (size_t)p.kblocks * p.dwp_bytes) != cudaSuccess) rc = fail(FD_ERR_CUDA, "cudaMalloc failed");
     if (rc == FD_OK) {
         const int tot = p.kblocks * 64;
-        if (dtype == FD_F16) pack_dwp_kernel<__half><<<(tot + 127) / 128, 128>>>(a.dw_w, a.dw_scale, a.dw_bias, (uint8_t*)bp->dwp, taps, g.c_in, p.kblocks, p.dwp_bytes);
-        else pack_dwp_kernel<__nv_bfloat16><<<(tot + 127) / 128, 128>>>(a.dw_w, a.dw_scale, a.dw_bias, (uint8_t*)bp->dwp, taps, g.c_in, p.kblocks, p.dwp_bytes);
+        if (dtype == FD_F16) pack_dwp_kernel<__half><<<(tot + 127) / 128, 128>>>(a.dw_w, a.dw_scale, a.dw_bias, (uint8_t*)bp->dwp, taps, g.c_in, p.kblocks, p.dwp_bytes, post);
+        else pack_dwp_kernel<__nv_bfloat16><<<(tot + 127) / 128, 128>>>(a.dw_w, a.dw_scale, a.dw_bias, (uint8_t*)bp->dwp, taps, g.c_in, p.kblocks, p.dwp_bytes, post);
         if (cudaGetLastError() != cudaSuccess) rc = fail(FD_ERR_CUDA, "pack_dwp_kernel launch failed");
     }
-    if (rc == FD_OK) rc = padded_copy(a.pw_scale, g.c_out, p.cpad_all, &bp->pw_scale);
-    if (rc == FD_OK) rc = padded_copy(a.pw_bias, g.c_out, p.cpad_all, &bp->pw_bias);
+    if (rc == FD_OK && cudaMalloc(&bp->pw_affine, (size_t)p.cpad_all * sizeof(float2)) != cudaSuccess) rc = fail(FD_ERR_CUDA, "cudaMalloc failed");
+    if (rc == FD_OK) {
+        pack_affine_kernel<<<(p.cpad_all + 127) / 128, 128>>>(a.pw_scale, a.pw_bias, bp->pw_affine, g.c_out, p.cpad_all, post);
+        if (cudaGetLastError() != cudaSuccess) rc = fail(FD_ERR_CUDA, "pack_affine_kernel launch failed");
+    }
     if (rc == FD_OK) rc = padded_copy(p.head ? head_w : a.pw_scale, p.head ? g.c_out : 0, p.cpad_all, &bp->head_w);
     if (rc == FD_OK && cudaDeviceSynchronize() != cudaSuccess) rc = fail(FD_ERR_CUDA, "parameter packing failed");
     if (rc != FD_OK) { block_tc_destroy(bp); return rc; }
-    p.dwp = bp->dwp; p.pw_scale = bp->pw_scale; p.pw_bias = bp->pw_bias; p.head_w = bp->head_w;
+    p.dwp = bp->dwp; p.pw_affine = bp->pw_affine; p.head_w = bp->head_w;
 
     // tensor maps
     const size_t es = 2;
@@ -749,10 +742,29 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { block_tc_destroy(bp); return fail(FD_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r)); }
     }
+    // output views for the TMA epilogue: plain NHWC, or the four (dy, dx) phases of the 2x nearest-upsampled tensor
+    memset(bp->tm_o, 0, sizeof(bp->tm_o));
+    p.epi_tma = (!p.head && tma_epilogue) ? 1 : 0;
+    p.epi_red = (p.epi_tma && a.skip != nullptr) ? 1 : 0;
+    if (p.epi_red && a.skip != a.out) { block_tc_destroy(bp); return fail(FD_ERR_STATE, "in-place skip accumulation needs out == skip"); }
+    if (p.epi_tma) {
+        const int up = g.upsample ? 2 : 1;
+        const cuuint64_t C = (cuuint64_t)g.c_out, W2 = (cuuint64_t)g.w_out * up, H2 = (cuuint64_t)g.h_out * up;
+        for (int d = 0; d < (g.upsample ? 4 : 1); ++d) {
+            char* base = reinterpret_cast<char*>(a.out) + ((size_t)(d >> 1) * W2 + (d & 1)) * C * es;
+            cuuint64_t dims[4] = {C, (cuuint64_t)g.w_out, (cuuint64_t)g.h_out, (cuuint64_t)g.n};
+            cuuint64_t strides[3] = {up * C * es, up * W2 * C * es, H2 * W2 * C * es};
+            cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)NI};
+            cuuint32_t estr[4] = {1, 1, 1, 1};
+            CUresult r = encode(&bp->tm_o[d], dt, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { block_tc_destroy(bp); return fail(FD_ERR_CUDA, "cuTensorMapEncodeTiled(output) failed: " + std::to_string((int)r)); }
+        }
+    }
     char buf[160];
-    snprintf(buf, sizeof(buf), "block_tc<k%d,s%d,%s>%s%s%s[n%dx%d,bn%d%s,kb%d,in%d]", g.ksize, g.stride, bp->tile ? "2x8x8" : "1x8x16",
-             g.upsample ? "+up2x" : "", a.skip ? "+skip" : "", p.head ? "+head" : "", p.n_cta, p.splits, p.bn,
-             p.b_resident ? "r" : "", p.kblocks, p.s_in);
+    snprintf(buf, sizeof(buf), "block_tc<k%d,s%d,%s>%s%s%s[n%dx%d,bn%d%s,kb%d,in%d,a%d]", g.ksize, g.stride, bp->tile ? "2x8x8" : "1x8x16",
+             g.upsample ? "+up2x" : "", a.skip ? (p.epi_red ? "+skip(red)" : "+skip") : "", p.head ? "+head" : (p.epi_tma ? "+tmast" : ""), p.n_cta, p.splits, p.bn,
+             p.b_resident ? "r" : "", p.kblocks, p.s_in, p.s_a);
     bp->name = buf;
     *out = bp;
     return FD_OK;

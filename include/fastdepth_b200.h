@@ -96,7 +96,11 @@ int fd_plan_set_stage_weights(fd_plan* plan, int stage,
  *                kernels where available (16-bit dtypes)            [default 1]
  *   "fold_head"  1 = apply decode_conv6 below the last upsample (exact: 1x1 conv/BN/ReLU
  *                commute with nearest upsampling) [default 1]
- *   "graph"      1 = replay fd_forward from a captured CUDA graph   [default 1]            */
+ *   "graph"      1 = replay fd_forward from a captured CUDA graph   [default 1]
+ *   "tma_epilogue" 1 = fused blocks write their output tiles with TMA tensor stores  [default 1]
+ *   "inplace_skip" 1 = decoder blocks ADD their upsampled output into the skip tensor in place
+ *                (TMA reduce-add); the skip source's stage buffer then holds the decoder output
+ *                after fd_forward (set 0 for stage-by-stage inspection)  [default 1]            */
 int fd_plan_set_option(fd_plan* plan, const char* name, int value);
 int fd_plan_get_option(fd_plan* plan, const char* name, int* value);
 
@@ -130,6 +134,13 @@ int fd_plan_step_info(fd_plan* plan, int step, int* stage, double* alg_bytes, do
  * ms_out[n_steps] = mean launch duration.  Synchronous. */
 int fd_plan_time_steps(fd_plan* plan, const void* x_dev, void* y_dev, void* stream,
                        int warmup, int iters, int flush_l2, float* ms_out);
+
+/* Debug: run stage `stage`'s fused block kernel once with its in-kernel timeline enabled and return
+ * the SM-clock stamps of CTA 0: rows = {TMA issue, dw start, dw math done, A tile published, MMA
+ * operands ready, MMA issued, epilogue start, epilogue done}, one column per K-block / item.
+ * The previous fd_forward's activations are reused as inputs. Synchronous. */
+int fd_plan_trace_stage(fd_plan* plan, int stage, void* y_dev, void* stream,
+                        unsigned long long* out_host, int cap, int* rows, int* cols);
 
 /* Per-image depth metrics on device (reference metrics.py:31-55 applied per image, as
  * main.py:40-41,80-82 does at batch size 1).  pred: [n, hw] of `dtype`; target: [n, hw] fp32.

@@ -1,0 +1,25 @@
+import sys, torch, numpy as np
+sys.path.insert(0,'/root/repo')
+import models
+from fastdepth_b200 import synthetic
+from fastdepth_b200.engine import SkipAddEngine
+sd=synthetic.synthetic_state_dict()
+m=models.MobileNetSkipAdd((224,224),pretrained=False); m.load_state_dict(sd); m=m.eval().cuda().half()
+eng=SkipAddEngine(m); eng.set_option('graph',0); m.__dict__['_fd_engine']=eng
+x=synthetic.synthetic_input(64,224,224).cuda().half()
+plan=eng.plan_for(x)
+y=torch.empty((64,1,224,224),dtype=torch.half,device='cuda')
+sp=torch.cuda.current_stream().cuda_stream
+plan.forward(x,y,sp); torch.cuda.synchronize()
+for st in [int(a) for a in sys.argv[1:]]:
+    tr=plan.trace_stage(st,y,sp)
+    t0=min(v.min() for v in tr.values() if len(v))
+    print('== stage',st,plan.names[st],[s['kernel'] for s in plan.steps() if s['stage']==st])
+    for k,v in tr.items():
+        v=v-t0
+        print('%-13s n=%3d first %s'%(k,len(v),' '.join('%6d'%a for a in v[:14])), ' ... last', ' '.join('%6d'%a for a in v[-3:]))
+    if len(tr['dw_start'])>4:
+        d=np.diff(tr['dw_start']); print('dw_start period: median %d  mean %d'%(np.median(d),d.mean()))
+        print('dw math (start->done) median', np.median(tr['dw_math_done']-tr['dw_start']), ' publish wait+write median', np.median(tr['a_published']-tr['dw_math_done']))
+        e=tr['epi_done']-tr['epi_start']; print('epilogue duration median',np.median(e), 'epi period median', np.median(np.diff(tr['epi_start'])) if len(e)>1 else -1)
+        print('mma ready->issued median', np.median(tr['mma_issued']-tr['mma_ready']))

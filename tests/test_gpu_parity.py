@@ -22,7 +22,7 @@ pytestmark = pytest.mark.gpu
 TOL = {torch.float32: 1e-3, torch.float16: 1e-2, torch.bfloat16: 1e-1}
 # intermediate tensors (bug localisation only): the 2 % 'hot' BN channels (gamma up to 3.5) amplify the
 # storage noise of single elements ~4x before the next layers average it out again
-STAGE_TOL = {torch.float32: 1e-3, torch.float16: 4e-2, torch.bfloat16: 3e-1}
+STAGE_TOL = {torch.float32: 1e-3, torch.float16: 6e-2, torch.bfloat16: 3e-1}
 
 
 def oracle():
@@ -85,6 +85,8 @@ def test_stage_by_stage(widths, dtype, path, fold):
     eng = SkipAddEngine(m)
     eng.set_option('path', path)
     eng.set_option('fold_head', fold)
+    eng.set_option('inplace_skip', 0)          # keep every stage buffer inspectable (skip sources are not overwritten)
+    eng.set_option('tma_epilogue', fold)       # fold=0 runs also exercise the LSU epilogue of the fused blocks
     m.__dict__['_fd_engine'] = eng
     with torch.no_grad():
         y = m(x.cuda().to(dtype))
