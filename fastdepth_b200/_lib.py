@@ -47,6 +47,7 @@ SIGNATURES = {
     'fd_plan_time_steps': (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p]),
     'fd_plan_trace_stage': (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int,
                                            _c_int_p, _c_int_p]),
+    'fd_debug_block_plan': (ctypes.c_int, [ctypes.c_int] * 8 + [_c_int_p, ctypes.c_int]),
     'fd_metrics_accumulate': (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp,
                                              ctypes.c_int, _vp]),
     'fd_plan_destroy': (None, [_vp]),

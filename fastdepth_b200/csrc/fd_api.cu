@@ -6,9 +6,12 @@
 #include <string>
 #include <vector>
 
+#include "fd_block_plan.h"
 #include "fd_common.cuh"
 
 namespace fd {
+
+BlockPlanOut block_tc_debug_plan(int ksize, int stride, int h_out, int w_out, int n, int c_in, int c_out, int head);
 
 // ---- error state -----------------------------------------------------------------------
 static thread_local std::string g_last_error;
@@ -593,8 +596,17 @@ int fd_plan_trace_stage(fd_plan* p, int stage, void* y_dev, void* stream, unsign
     int rc = ensure_steps(p);
     if (rc) return rc;
     if (!p->stages[stage].tc) return fail(FD_ERR_STATE, "stage does not run the fused block kernel");
-    if (cap < 8 * 256) return fail(FD_ERR_INVALID, "trace buffer too small (need 2048 entries)");
+    if (cap < 12 * 256) return fail(FD_ERR_INVALID, "trace buffer too small (need 3072 entries)");
     return block_tc_trace(p->stages[stage].tc, (cudaStream_t)stream, y_dev, out_host, rows, cols);
+}
+
+int fd_debug_block_plan(int ksize, int stride, int h_out, int w_out, int n, int c_in, int c_out, int head, int* out, int cap) {
+    if (!out || cap < 16) return fail(FD_ERR_INVALID, "need an int[16] output");
+    const BlockPlanOut q = block_tc_debug_plan(ksize, stride, h_out, w_out, n, c_in, c_out, head);
+    const int v[16] = {q.ok, q.splits, q.n_cta, q.items, q.kblocks, q.s_in, q.s_a, q.s_b, q.bn, q.nb, q.b_resident, q.epi_groups,
+                       q.n_stg, q.smem_bytes, q.tmem_cols, q.in_stage_stride};
+    for (int i = 0; i < 16; ++i) out[i] = v[i];
+    return FD_OK;
 }
 
 int fd_metrics_accumulate(const void* pred_dev, const float* target_dev, int dtype, int n, int hw, double* sums_dev,

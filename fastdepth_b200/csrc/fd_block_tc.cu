@@ -28,6 +28,7 @@
 #include <new>
 #include <string>
 
+#include "fd_block_plan.h"
 #include "fd_tc_common.cuh"
 
 namespace fd {
@@ -67,7 +68,8 @@ struct TcParams {
     int in_stage_stride;  // in_stage_bytes + dw parameter block, rounded to 128
     int dwp_bytes;        // bytes of one K-block's depthwise parameter block
     int cpad_all;         // n_cta * splits: padded length of the pointwise BN vectors
-    int n_stg;            // epilogue staging buffers (16 KB each): 2, or 1 when shared memory is tight
+    int n_stg;            // epilogue staging tiles (16 KB each) in total: epi_groups x (2 or 1)
+    int epi_groups;       // 2: two groups of four epilogue warps take alternate items; 1: one group takes all (smem is tight)
     int epi_tma;          // 1: staging tiles leave through TMA tensor stores (4 strided views for nearest-x2 upsampling)
     int epi_red;          // 1: ... as element-wise ADD into the skip tensor, which then IS the block's output (in place)
     unsigned long long mg_splits, mg_tx, mg_ty;   // 2^40 / d reciprocals for the item -> tile decode
@@ -75,7 +77,7 @@ struct TcParams {
                           //   (scale and bias pre-divided by 6 for ReLU6 stages: y = 6 * sat(acc*s/6 + b/6))
     const float2* pw_affine;  // [cpad_all] (scale, bias) pairs, same /6 convention
     const float* head_w;  // [cpad_all]
-    unsigned long long* trace;   // debug timeline (fd_plan_trace_step) or nullptr: [8 rows][TC_TRACE_N] SM clocks of CTA 0
+    unsigned long long* trace;   // debug timeline (fd_plan_trace_stage) or nullptr: [12 rows][TC_TRACE_N] SM clocks of CTA 0
 };
 
 // shared-memory bookkeeping block (after the operand stages)
@@ -131,7 +133,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
     const uint32_t in_off = b_off + p.s_b * p.b_stage_bytes;
     const uint32_t stg_off = (in_off + p.s_in * p.in_stage_stride + 1023u) & ~1023u;   // epilogue staging: [128 px][64 ch] 16-bit, SW128 atoms
     const uint32_t pw_off = stg_off + (uint32_t)p.n_stg * 16384u;
-    const uint32_t bar_off = pw_off + 3u * (uint32_t)p.cpad_all * 4u;
+    const uint32_t bar_off = pw_off + (p.head ? 3u : 2u) * (uint32_t)p.cpad_all * 4u;
     TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem + bar_off);
     float2* s_pw_affine = reinterpret_cast<float2*>(smem + pw_off);           // (scale, bias) per output channel
     float* s_head_w = reinterpret_cast<float*>(s_pw_affine + p.cpad_all);
@@ -142,7 +144,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         for (int i = 0; i < TC_MAX_IN; ++i) { mbar_init(smem_u32(&bars->in_full[i]), 1); mbar_init(smem_u32(&bars->in_empty[i]), TC_DW_WARPS); }
         for (int i = 0; i < TC_MAX_A; ++i) { mbar_init(smem_u32(&bars->a_full[i]), TC_DW_WARPS); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
         for (int i = 0; i < TC_MAX_B; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), TC_EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), TC_EPI_WARPS / 2); }
         fence_barrier_init();
     }
     if (warp == TC_WARP_MMA) tmem_alloc(smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);     // MMA warp owns TMEM
@@ -153,7 +155,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
     }
     for (int i = threadIdx.x; i < p.cpad_all; i += TC_THREADS) {          // pointwise BN affine (+ head weights) -> smem
         s_pw_affine[i] = p.pw_affine[i];
-        s_head_w[i] = p.head ? p.head_w[i] : 0.f;
+        if (p.head) s_head_w[i] = p.head_w[i];
     }
     tc_fence_before();
     __syncthreads();
@@ -162,11 +164,12 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
 
     if (warp == TC_WARP_TMA) {
         // =========================== TMA producer ===========================
+        // two independent single-thread loops in one warp: lane 0 streams input tiles (+ depthwise parameter blocks),
+        // lane 1 streams pointwise-weight blocks, so a full weight ring never holds back the input prefetch
         if (lane == 0) {
-            Ring rin, rb;
+            Ring rin;
             int tr = 0;
-            bool first = true;
-            for (int w = blockIdx.x; w < p.items; w += gridDim.x, first = false) {
+            for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
                 const ItemCoord c = decode_item(p, w, NI, TH, TW);
                 for (int kb = 0; kb < p.kblocks; ++kb, rin.next((uint32_t)p.s_in)) {
                     const uint32_t s = rin.s, ph = rin.ph;
@@ -178,7 +181,15 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                               reinterpret_cast<const uint8_t*>(p.dwp) + (size_t)kb * p.dwp_bytes, (uint32_t)p.dwp_bytes,
                               smem_u32(&bars->in_full[s]));
                     TC_TRACE(0, tr); ++tr;
-                    if (p.b_resident && !first) continue;
+                }
+            }
+        } else if (lane == 1) {
+            Ring rb;
+            bool first = true;
+            for (int w = blockIdx.x; w < p.items; w += gridDim.x, first = false) {
+                if (p.b_resident && !first) break;
+                const int n0 = (w - (int)fdiv40((uint32_t)w, p.mg_splits) * p.splits) * p.n_cta;
+                for (int kb = 0; kb < p.kblocks; ++kb)
                     for (int nbi = 0; nbi < p.nb; ++nbi) {
                         uint32_t sb;
                         if (p.b_resident) {
@@ -190,9 +201,8 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                         }
                         mbar_expect_tx(smem_u32(&bars->b_full[sb]), (uint32_t)p.b_stage_bytes);
                         tma_load_2d(smem_base + b_off + sb * p.b_stage_bytes, &tm_w, smem_u32(&bars->b_full[sb]), kb * TC_KBLK,
-                                    c.n0 + nbi * p.bn);
+                                    n0 + nbi * p.bn);
                     }
-                }
             }
         }
     } else if (warp == TC_WARP_MMA) {
@@ -313,75 +323,83 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         }
     } else {
         // =========================== epilogue warps ===========================
+        // Two independent groups of four warps; group g drains TMEM accumulator g, i.e. every second item, so one
+        // group's TMEM-load / barrier latency overlaps the other group's math and stores.
         const int ew = warp - TC_WARP_EPI0;
-        const int q = ew & 3, hsel = ew >> 2;              // TMEM lane quarter (== warp % 4), column-batch parity
-        const int m = q * 32 + lane;
+        const int q = ew & 3, grp = ew >> 2;               // TMEM lane quarter (== warp % 4), group / accumulator index
+        const int m = q * 32 + lane;                       // accumulator row == pixel of the tile
         const int e_ni = m / (TH * TW), e_ty = (m / TW) % TH, e_tx = m % TW;
-        const int batches = (p.n_cta + 31) >> 5;           // 32 accumulator columns per batch
+        const uint32_t bar_id = 1u + (uint32_t)grp;        // named barrier of this group (128 threads)
+        const bool elected = q == 0 && lane == 0;          // issues this group's tensor stores
         T* __restrict__ outp = reinterpret_cast<T*>(p.out);
         const T* __restrict__ skipp = reinterpret_cast<const T*>(p.skip);
-        Ring racc;
+        const int ngrp = p.epi_groups;                     // 2, or 1 when shared memory is tight (group 1 then idles)
+        const int n_stg_g = p.head ? 0 : p.n_stg / ngrp;   // staging tiles of this group: 1 or 2
+        const uint32_t stg_grp = stg_off + (uint32_t)grp * (uint32_t)n_stg_g * 16384u;
+        uint32_t ab = ngrp == 2 ? (uint32_t)grp : 0u, pa = 0;   // accumulator buffer and its mbarrier phase
         int tr = 0;
         uint32_t stg_flip = 0;
-        for (int w = blockIdx.x; w < p.items; w += gridDim.x, racc.next((uint32_t)p.nacc)) {
+        for (int w = blockIdx.x + grp * gridDim.x; grp < ngrp && w < p.items; w += ngrp * gridDim.x) {
             const ItemCoord c = decode_item(p, w, NI, TH, TW);
-            const uint32_t ab = racc.s, pa = racc.ph;
             const int img = c.img0 + e_ni, oy = c.oy0 + e_ty, ox = c.ox0 + e_tx;
             const bool valid = img < p.n && oy < p.h_out && ox < p.w_out;
             mbar_wait(smem_u32(&bars->acc_full[ab]), pa);
             tc_fence_after();
-            if (ew == 0 && lane == 0) TC_TRACE(6, tr);
+            if (grp == 0 && elected) TC_TRACE(6, tr);
             const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + ab * (uint32_t)p.n_cta;
 
             if (!p.head) {
-                // Two phases per block of 64 output channels so that global memory sees whole 128-byte lines:
-                //  A: TMEM -> BN affine + act -> 16-bit -> shared staging tile [128 pixels][64 ch] (16-byte chunks XOR-swizzled)
-                //  B: 8 consecutive lanes move one pixel's 128 contiguous bytes (x4 positions + skip for decoder blocks)
+                // per block of 64 output channels:
+                //  A: TMEM -> BN affine + act -> 16-bit -> shared staging tile [128 pixels][64 ch] (16-byte chunks XOR-swizzled
+                //     exactly like a SWIZZLE_128B tensor-map box)
+                //  B: the tile leaves through TMA tensor stores (or, as a fallback, coalesced 16-byte LSU stores)
                 const int nblk = (p.n_cta + 63) >> 6;
                 for (int cb = 0; cb < nblk; ++cb) {
-                    uint8_t* stg = smem + stg_off + (p.n_stg == 2 ? (stg_flip & 1u) * 16384u : 0u);
+                    uint8_t* stg = smem + stg_grp + (n_stg_g == 2 ? (stg_flip & 1u) * 16384u : 0u);
                     ++stg_flip;
-                    if (p.n_stg == 1 && (cb > 0 || stg_flip > 1)) {      // single staging buffer: wait until it is free again
-                        if (p.epi_tma && ew == 0 && lane == 0) bulk_wait_read0();
-                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (n_stg_g == 1 && stg_flip > 1) {                  // single staging buffer: wait until it is free again
+                        if (p.epi_tma && elected) bulk_wait_read0();
+                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                     }
-                    const int col0 = cb * 64 + hsel * 32;                 // first accumulator column of this warp
-                    if (col0 < p.n_cta) {
-                        uint32_t r[32];
-                        const bool full = col0 + 32 <= p.n_cta;           // n_cta is a multiple of 16
-                        if (full) tmem_ld32_sync(t_lane + col0, r);
-                        else tmem_ld16_sync(t_lane + col0, r);
-                        if (cb == nblk - 1) {                             // last TMEM read of this item: release the accumulator early
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));
-                        }
-                        uint8_t* row = stg + m * 128;
+                    uint8_t* row = stg + m * 128;
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {                     // 8 channels -> one 16-byte chunk
-                            if (g >= 2 && !full) break;
-                            uint32_t pk[4];
+                    for (int half = 0; half < 2; ++half) {
+                        const int col0 = cb * 64 + half * 32;             // first accumulator column of this half block
+                        if (col0 < p.n_cta) {
+                            uint32_t r[32];
+                            const bool full = col0 + 32 <= p.n_cta;       // n_cta is a multiple of 16
+                            if (full) tmem_ld32_sync(t_lane + col0, r);
+                            else tmem_ld16_sync(t_lane + col0, r);
+                            if (grp == 0 && elected && cb == 0 && half == 0) TC_TRACE(8, tr);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float4 af = *reinterpret_cast<const float4*>(s_pw_affine + c.n0 + col0 + g * 8 + 2 * j);   // s0, b0, s1, b1
-                                pk[j] = MF::pack(affine_act<RELU6>(__uint_as_float(r[g * 8 + 2 * j]), af.x, af.y),
-                                                 affine_act<RELU6>(__uint_as_float(r[g * 8 + 2 * j + 1]), af.z, af.w));
+                            for (int g = 0; g < 4; ++g) {                 // 8 channels -> one 16-byte chunk
+                                if (g >= 2 && !full) break;
+                                uint32_t pk[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float4 af = *reinterpret_cast<const float4*>(s_pw_affine + c.n0 + col0 + g * 8 + 2 * j);   // s0, b0, s1, b1
+                                    pk[j] = MF::pack(affine_act<RELU6>(__uint_as_float(r[g * 8 + 2 * j]), af.x, af.y),
+                                                     affine_act<RELU6>(__uint_as_float(r[g * 8 + 2 * j + 1]), af.z, af.w));
+                                }
+                                *reinterpret_cast<uint4*>(row + (((half * 4 + g) ^ (m & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                             }
-                            *reinterpret_cast<uint4*>(row + (((hsel * 4 + g) ^ (m & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         }
-                    } else if (cb == nblk - 1) {
+                    }
+                    if (cb == nblk - 1) {                                 // last TMEM read of this item: release the accumulator early
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));
                     }
                     if (p.epi_tma) {
-                        // the tile leaves through the TMA: one elected thread, asynchronous, whole 128-byte lines, image
-                        // borders and channel tails clipped by the hardware.  Before anyone may overwrite the other
-                        // staging buffer its previous store must have finished READING shared memory.
+                        // one elected thread per group, asynchronous, whole 128-byte lines, image borders and channel
+                        // tails clipped by the hardware.  Before anyone may overwrite the other staging buffer its previous
+                        // store must have finished READING shared memory.
                         fence_proxy_async();
-                        if (ew == 0 && lane == 0) bulk_wait_read0();
-                        asm volatile("bar.sync 1, 256;" ::: "memory");    // staging tile complete + other buffer free
-                        if (ew == 0 && lane == 0) {
+                        if (grp == 0 && elected && cb == 0) TC_TRACE(9, tr);
+                        if (elected) bulk_wait_read0();
+                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");    // staging tile complete + other buffer free
+                        if (grp == 0 && elected && cb == 0) TC_TRACE(10, tr);
+                        if (elected) {
                             const uint32_t src = smem_u32(stg);
                             const int cc = c.n0 + cb * 64;
                             if (!p.upsample) {
@@ -398,26 +416,27 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                                 tma_reduce_add_4d(&tm_o3, src, cc, c.ox0, c.oy0, c.img0);
                             }
                             bulk_commit_group();
+                            if (grp == 0 && cb == 0) TC_TRACE(11, tr);
                         }
                         continue;
                     }
-                    asm volatile("bar.sync 1, 256;" ::: "memory");        // staging tile complete
-                    const int et = ew * 32 + lane;                        // 0..255 over the 8 epilogue warps
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");        // staging tile complete
+                    const int et = q * 32 + lane;                         // 0..127 over the group's four warps
                     const int ch = et & 7;                                // 16-byte chunk within the 64-channel block
                     const int ccol = cb * 64 + ch * 8;                    // accumulator column of that chunk
                     const bool cok = ccol < p.n_cta && c.n0 + ccol + 8 <= p.c_out;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int rr = (et >> 3) + 32 * k;                // pixel row of the tile
+                    for (int k = 0; k < 8; ++k) {
+                        const int rr = (et >> 3) + 16 * k;                // pixel row of the tile
                         const int r_ni = rr / (TH * TW), r_ty = (rr / TW) % TH, r_tx = rr % TW;
-                        const int img = c.img0 + r_ni, oy = c.oy0 + r_ty, ox = c.ox0 + r_tx;
-                        if (!(cok && img < p.n && oy < p.h_out && ox < p.w_out)) continue;
+                        const int pimg = c.img0 + r_ni, poy = c.oy0 + r_ty, pox = c.ox0 + r_tx;
+                        if (!(cok && pimg < p.n && poy < p.h_out && pox < p.w_out)) continue;
                         const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
                         if (!p.upsample) {
-                            *reinterpret_cast<uint4*>(outp + (((size_t)img * p.h_out + oy) * p.w_out + ox) * p.c_out + c.n0 + ccol) = v;
+                            *reinterpret_cast<uint4*>(outp + (((size_t)pimg * p.h_out + poy) * p.w_out + pox) * p.c_out + c.n0 + ccol) = v;
                         } else {
                             const int w2 = 2 * p.w_out;
-                            const size_t off00 = (((size_t)img * 2 * p.h_out + 2 * oy) * w2 + 2 * ox) * p.c_out + c.n0 + ccol;
+                            const size_t off00 = (((size_t)pimg * 2 * p.h_out + 2 * poy) * w2 + 2 * pox) * p.c_out + c.n0 + ccol;
                             size_t off[4];
 #pragma unroll
                             for (int d = 0; d < 4; ++d) off[d] = off00 + ((size_t)(d >> 1) * w2 + (d & 1)) * p.c_out;
@@ -445,8 +464,9 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                         }
                     }
                 }
-            } else if (hsel == 0) {
+            } else {
                 // decode_conv6 folded below the last upsample: dot over this block's (<= 64) output channels
+                const int batches = (p.n_cta + 31) >> 5;
                 float dot = 0.f;
                 for (int b = 0; b < batches; ++b) {
                     uint32_t r[32];
@@ -466,6 +486,9 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                         dot = fmaf(rq.y, hw.y, dot);
                     }
                 }
+                tc_fence_before();                                       // accumulator drained
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));
                 if (valid) {
                     const float y = apply_act(fmaf(dot, p.head_scale, p.head_bias), p.head_act);
                     const uint32_t yy = MF::pack(y, y);
@@ -474,14 +497,10 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                     *reinterpret_cast<uint32_t*>(ho + 2 * p.w_out) = yy;
                 }
             }
-            if (p.head) {                                            // (the non-head path released it after its last TMEM read)
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));
-            }
-            if (ew == 0 && lane == 0) { TC_TRACE(7, tr); ++tr; }
+            if (grp == 0 && elected) { TC_TRACE(7, tr); ++tr; }
+            if (ngrp == 2) { pa ^= 1u; } else { ab ^= 1u; if (ab == 0u) pa ^= 1u; }
         }
-        if (p.epi_tma && ew == 0 && lane == 0) bulk_wait_all();      // all tensor stores of this CTA have landed
+        if (p.epi_tma && elected) bulk_wait_all();                       // all tensor stores of this group have landed
     }
 
     tc_fence_before();
@@ -573,10 +592,21 @@ int block_tc_launch(BlockTcPlan* bp, cudaStream_t st, void* head_out) {
 
 const char* block_tc_name(BlockTcPlan* bp) { return bp->name.c_str(); }
 
+BlockPlanOut block_tc_debug_plan(int ksize, int stride, int h_out, int w_out, int n, int c_in, int c_out, int head) {
+    StageGeom g{};
+    g.h_out = h_out; g.w_out = w_out;
+    BlockPlanIn q{};
+    q.ksize = ksize; q.stride = stride; q.tile = pick_tile(g); q.c_in = c_in; q.c_out = c_out; q.head = head;
+    const int NI = q.tile ? 2 : 1, TW = q.tile ? 8 : 16;
+    q.n_tiles = ((w_out + TW - 1) / TW) * ((h_out + 7) / 8) * ((n + NI - 1) / NI);
+    q.barrier_bytes = (int)sizeof(TcBarriers);
+    return plan_block(q);
+}
+
 // debug: run once with the timeline enabled; out_host[8 * TC_TRACE_N] SM clocks of CTA 0 (0 = slot unused)
 int block_tc_trace(BlockTcPlan* bp, cudaStream_t st, void* head_out, unsigned long long* out_host, int* rows, int* cols) {
     unsigned long long* dev = nullptr;
-    const size_t bytes = 8 * TC_TRACE_N * sizeof(unsigned long long);
+    const size_t bytes = 12 * TC_TRACE_N * sizeof(unsigned long long);
     FD_CUDA_OK(cudaMalloc(&dev, bytes));
     FD_CUDA_OK(cudaMemsetAsync(dev, 0, bytes, st));
     bp->p.trace = dev;
@@ -585,7 +615,7 @@ int block_tc_trace(BlockTcPlan* bp, cudaStream_t st, void* head_out, unsigned lo
     if (rc == FD_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(FD_ERR_CUDA, "trace run failed");
     if (rc == FD_OK) cudaMemcpy(out_host, dev, bytes, cudaMemcpyDeviceToHost);
     cudaFree(dev);
-    *rows = 8; *cols = TC_TRACE_N;
+    *rows = 12; *cols = TC_TRACE_N;
     return rc;
 }
 
@@ -646,55 +676,19 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
     p.head = head_w != nullptr; p.head_act = head_act; p.head_scale = head_scale; p.head_bias = head_bias;
     p.skip = a.skip; p.out = a.out; p.head_out = head_out;
 
-    // split the output channels into items until there are enough items for the 148 SMs (each item
-    // recomputes the cheap depthwise half) and the per-item accumulator fits TMEM
-    const int cout_pad = (g.c_out + 15) / 16 * 16;
-    int splits = 1;
-    while ((cout_pad + splits - 1) / splits > 256 || (n_tiles * splits < 148 && (cout_pad / (splits * 2)) >= 64 && !p.head)) splits *= 2;
-    p.n_cta = ((cout_pad + splits - 1) / splits + 15) / 16 * 16;
-    // with several splits every item's channel range must end on a 64-channel boundary: the epilogue moves whole
-    // [128 px][64 ch] tiles and must not touch a neighbouring split's columns
-    if (splits > 1) p.n_cta = (p.n_cta + 63) / 64 * 64;
-    splits = (cout_pad + p.n_cta - 1) / p.n_cta;
-    p.splits = splits;
-    p.items = n_tiles * splits;
-    p.nacc = 2;                                       // n_cta <= 256 -> two accumulators fit 512 columns
-    p.tmem_cols = 32;
-    while (p.tmem_cols < p.nacc * p.n_cta) p.tmem_cols *= 2;
-    p.in_stage_bytes = NI * IH * IW * 128;
+    BlockPlanIn pin{};
+    pin.ksize = g.ksize; pin.stride = g.stride; pin.tile = bp->tile; pin.c_in = g.c_in; pin.c_out = g.c_out; pin.n_tiles = n_tiles;
+    pin.head = p.head; pin.barrier_bytes = (int)sizeof(TcBarriers);
+    const BlockPlanOut po = plan_block(pin);
+    if (!po.ok) { delete bp; return fail(FD_ERR_UNSUPPORTED, "fused block does not fit shared memory"); }
+    const int splits = po.splits;
+    p.n_cta = po.n_cta; p.splits = po.splits; p.items = po.items; p.nacc = 2; p.tmem_cols = po.tmem_cols;
+    p.in_stage_bytes = po.in_stage_bytes; p.dwp_bytes = po.dwp_bytes; p.in_stage_stride = po.in_stage_stride; p.cpad_all = po.cpad_all;
+    p.s_a = po.s_a; p.n_stg = po.n_stg; p.epi_groups = po.epi_groups; p.s_in = po.s_in; p.s_b = po.s_b; p.bn = po.bn; p.nb = po.nb;
+    p.b_resident = po.b_resident; p.b_stage_bytes = po.b_stage_bytes;
+    bp->smem_bytes = (size_t)po.smem_bytes;
     const int taps = g.ksize * g.ksize;
-    p.dwp_bytes = taps * 128 + 512;
-    p.in_stage_stride = (p.in_stage_bytes + p.dwp_bytes + 127) / 128 * 128;
-    p.cpad_all = p.n_cta * splits;
-    // shared-memory plan: try the deepest A ring / double staging first, fall back when the input stages are large
-    // (stride-2 blocks stage 72 KB per K-block).  A deep A ring hides the serial latency of the MMA issue thread.
-    bool fits = false;
-    for (int attempt = 0; attempt < 4 && !fits; ++attempt) {
-        p.s_a = attempt == 0 ? 4 : (attempt == 1 ? 3 : 2);
-        p.n_stg = p.head ? 0 : (attempt <= 1 ? 2 : (attempt == 2 ? 2 : 1));
-        const int avail = 212 * 1024 - (int)sizeof(TcBarriers) - 2048 - p.s_a * TC_A_STAGE_BYTES - 3 * p.cpad_all * 4 - p.n_stg * 16384;
-        // weights: resident when the whole [cin_pad x n_cta] matrix is small and every item uses the same one
-        p.bn = p.n_cta < 256 ? p.n_cta : 256;
-        p.nb = (p.n_cta + p.bn - 1) / p.bn;
-        const int w_all = p.kblocks * p.nb * p.bn * 128;
-        p.b_resident = (splits == 1 && p.kblocks * p.nb <= TC_MAX_B && w_all <= 64 * 1024 && w_all + 2 * p.in_stage_stride <= avail) ? 1 : 0;
-        if (p.b_resident) {
-            p.s_b = p.kblocks * p.nb;
-        } else {
-            p.s_b = 2;
-            while (p.bn > 16 && p.s_b * p.bn * 128 + 2 * p.in_stage_stride > avail) p.bn = (p.bn / 2 + 15) / 16 * 16;
-            p.nb = (p.n_cta + p.bn - 1) / p.bn;
-            while (p.s_b < 3 && (p.s_b + 1) * p.bn * 128 + 4 * p.in_stage_stride <= avail && p.s_b < p.kblocks * p.nb) ++p.s_b;
-        }
-        p.b_stage_bytes = p.bn * 128;
-        p.s_in = (avail - p.s_b * p.b_stage_bytes) / p.in_stage_stride;
-        if (p.s_in > TC_MAX_IN) p.s_in = TC_MAX_IN;
-        fits = p.s_in >= 2 && (p.bn >= 64 || p.bn == p.n_cta);
-        if (!fits && attempt == 3) fits = p.s_in >= 1;
-    }
-    if (!fits) { delete bp; return fail(FD_ERR_UNSUPPORTED, "fused block does not fit shared memory"); }
-    bp->smem_bytes = (size_t)p.s_a * TC_A_STAGE_BYTES + (size_t)p.s_b * p.b_stage_bytes + (size_t)p.s_in * p.in_stage_stride +
-                     (size_t)p.n_stg * 16384 + 1024 + 3 * (size_t)p.cpad_all * 4 + sizeof(TcBarriers) + 1024;
+    (void)splits;
     int sms = 148;
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
     bp->grid = dim3((unsigned)(p.items < sms ? p.items : sms), 1, 1);
@@ -762,9 +756,9 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
         }
     }
     char buf[160];
-    snprintf(buf, sizeof(buf), "block_tc<k%d,s%d,%s>%s%s%s[n%dx%d,bn%d%s,kb%d,in%d,a%d]", g.ksize, g.stride, bp->tile ? "2x8x8" : "1x8x16",
+    snprintf(buf, sizeof(buf), "block_tc<k%d,s%d,%s>%s%s%s[n%dx%d,bn%d%s,kb%d,in%d,a%d,e%dx%d]", g.ksize, g.stride, bp->tile ? "2x8x8" : "1x8x16",
              g.upsample ? "+up2x" : "", a.skip ? (p.epi_red ? "+skip(red)" : "+skip") : "", p.head ? "+head" : (p.epi_tma ? "+tmast" : ""), p.n_cta, p.splits, p.bn,
-             p.b_resident ? "r" : "", p.kblocks, p.s_in, p.s_a);
+             p.b_resident ? "r" : "", p.kblocks, p.s_in, p.s_a, p.epi_groups, p.head ? 0 : p.n_stg / p.epi_groups);
     bp->name = buf;
     *out = bp;
     return FD_OK;

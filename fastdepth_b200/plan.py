@@ -181,12 +181,13 @@ class Plan:
     def trace_stage(self, stage, y, stream_ptr):
         """Debug timeline of one fused block kernel (CTA 0): dict row-name -> list of SM clock stamps."""
         import numpy as np
-        buf = (ctypes.c_uint64 * 2048)()
+        buf = (ctypes.c_uint64 * 3072)()
         rows, cols = ctypes.c_int(), ctypes.c_int()
-        _lib.check(self.lib.fd_plan_trace_stage(self.handle, stage, y.data_ptr(), stream_ptr, buf, 2048,
+        _lib.check(self.lib.fd_plan_trace_stage(self.handle, stage, y.data_ptr(), stream_ptr, buf, 3072,
                                                 ctypes.byref(rows), ctypes.byref(cols)))
         a = np.frombuffer(buf, dtype=np.uint64).reshape(rows.value, cols.value).astype(np.int64)
-        names = ('tma_issue', 'dw_start', 'dw_math_done', 'a_published', 'mma_ready', 'mma_issued', 'epi_start', 'epi_done')
+        names = ('tma_issue', 'dw_start', 'dw_math_done', 'a_published', 'mma_ready', 'mma_issued', 'epi_start', 'epi_done',
+                 'epi_tmem_loaded', 'epi_staged', 'epi_barrier', 'epi_store_issued')
         return {n: a[i][a[i] > 0] for i, n in enumerate(names)}
 
     def stage_tensor(self, stage, which=0):

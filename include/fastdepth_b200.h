@@ -142,6 +142,12 @@ int fd_plan_time_steps(fd_plan* plan, const void* x_dev, void* y_dev, void* stre
 int fd_plan_trace_stage(fd_plan* plan, int stage, void* y_dev, void* stream,
                         unsigned long long* out_host, int cap, int* rows, int* cols);
 
+/* Debug (host only, needs no GPU): the shared-memory / pipeline plan the fused block kernel would use for one
+ * block.  out[16] = {ok, splits, n_cta, items, kblocks, s_in, s_a, s_b, bn, nb, b_resident, epi_groups, n_stg,
+ * smem_bytes, tmem_cols, in_stage_stride}. */
+int fd_debug_block_plan(int ksize, int stride, int h_out, int w_out, int n, int c_in, int c_out, int head,
+                        int* out, int cap);
+
 /* Per-image depth metrics on device (reference metrics.py:31-55 applied per image, as
  * main.py:40-41,80-82 does at batch size 1).  pred: [n, hw] of `dtype`; target: [n, hw] fp32.
  * Adds, for each image, its 10 metric values into sums_dev[0..9] (order: irmse, imae, mse,

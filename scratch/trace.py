@@ -23,3 +23,8 @@ for st in [int(a) for a in sys.argv[1:]]:
         print('dw math (start->done) median', np.median(tr['dw_math_done']-tr['dw_start']), ' publish wait+write median', np.median(tr['a_published']-tr['dw_math_done']))
         e=tr['epi_done']-tr['epi_start']; print('epilogue duration median',np.median(e), 'epi period median', np.median(np.diff(tr['epi_start'])) if len(e)>1 else -1)
         print('mma ready->issued median', np.median(tr['mma_issued']-tr['mma_ready']))
+        if len(tr['epi_tmem_loaded'])>2:
+            n=min(len(tr['epi_start']),len(tr['epi_tmem_loaded']),len(tr['epi_staged']),len(tr['epi_barrier']),len(tr['epi_store_issued']))
+            a=[tr[k][:n] for k in ('epi_start','epi_tmem_loaded','epi_staged','epi_barrier','epi_store_issued','epi_done')]
+            print('epilogue phases (median cycles): ld %d | math+sts+fence %d | wait_read+barrier %d | store issue %d | rest %d'%tuple(np.median(a[i+1]-a[i]) for i in range(5)))
+            print('acc_full wait: epi_start - prev epi_done median', np.median(tr['epi_start'][1:n]-tr['epi_done'][:n-1]))
