@@ -87,6 +87,11 @@ struct fd_plan {
     bool steps_valid = false;
     int opt_path = 1, opt_fold_head = 1, opt_graph = 1, opt_tma_epilogue = 1, opt_inplace_skip = 1;
     size_t workspace_bytes = 0;
+    // fd_pipeline_*: host batches flow H2D -> forward -> D2H through kPipeSlots device slots on three streams
+    struct PipeSlot { void* x = nullptr; void* y = nullptr; cudaEvent_t up = nullptr, done = nullptr, down = nullptr; bool busy = false; };
+    PipeSlot pipe[3];
+    cudaStream_t pipe_h2d = nullptr, pipe_run = nullptr, pipe_d2h = nullptr;
+    unsigned long long pipe_next = 0;    // next ticket
     void* stage_x = nullptr;             // device staging for fd_forward_host
     void* stage_y = nullptr;
     void* l2_flush = nullptr;
@@ -495,6 +500,63 @@ int fd_forward_host(fd_plan* p, const void* x_host, void* y_host, void* stream) 
     return FD_OK;
 }
 
+static const int kPipeSlots = 3;
+
+int fd_pipeline_submit(fd_plan* p, const void* x_host, void* y_host, unsigned long long* ticket) {
+    if (!p || !x_host || !y_host || !ticket) return fail(FD_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(p->device);
+    const size_t es = dtype_size(p->dtype);
+    const size_t xb = (size_t)p->n * 3 * p->h * p->w * es, yb = (size_t)p->n * p->h * p->w * es;
+    if (!p->pipe_h2d) {
+        FD_CUDA_OK(cudaStreamCreateWithFlags(&p->pipe_h2d, cudaStreamNonBlocking));
+        FD_CUDA_OK(cudaStreamCreateWithFlags(&p->pipe_run, cudaStreamNonBlocking));
+        FD_CUDA_OK(cudaStreamCreateWithFlags(&p->pipe_d2h, cudaStreamNonBlocking));
+        for (auto& sl : p->pipe) {
+            int rc = dev_alloc(p, &sl.x, xb);
+            if (rc) return rc;
+            if ((rc = dev_alloc(p, &sl.y, yb))) return rc;
+            FD_CUDA_OK(cudaEventCreateWithFlags(&sl.up, cudaEventDisableTiming));
+            FD_CUDA_OK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+            FD_CUDA_OK(cudaEventCreateWithFlags(&sl.down, cudaEventDisableTiming));
+        }
+    }
+    const unsigned long long t = p->pipe_next;
+    fd_plan::PipeSlot& sl = p->pipe[t % kPipeSlots];
+    if (sl.busy) {                                   // slot still owned by ticket t - kPipeSlots: wait for its download
+        FD_CUDA_OK(cudaEventSynchronize(sl.down));
+        sl.busy = false;
+    }
+    // upload on the copy-in stream; the forward waits for it; the download waits for the forward
+    FD_CUDA_OK(cudaMemcpyAsync(sl.x, x_host, xb, cudaMemcpyHostToDevice, p->pipe_h2d));
+    FD_CUDA_OK(cudaEventRecord(sl.up, p->pipe_h2d));
+    FD_CUDA_OK(cudaStreamWaitEvent(p->pipe_run, sl.up, 0));
+    int rc = fd_forward(p, sl.x, sl.y, p->pipe_run);
+    if (rc) return rc;
+    FD_CUDA_OK(cudaEventRecord(sl.done, p->pipe_run));
+    FD_CUDA_OK(cudaStreamWaitEvent(p->pipe_d2h, sl.done, 0));
+    FD_CUDA_OK(cudaMemcpyAsync(y_host, sl.y, yb, cudaMemcpyDeviceToHost, p->pipe_d2h));
+    FD_CUDA_OK(cudaEventRecord(sl.down, p->pipe_d2h));
+    // (a slot is only re-filled after the host saw its previous download complete, which implies its forward has
+    //  finished reading sl.x -- no stream-level dependency is needed, and adding one would serialise the uploads)
+    sl.busy = true;
+    *ticket = t;
+    p->pipe_next = t + 1;
+    return FD_OK;
+}
+
+int fd_pipeline_wait(fd_plan* p, unsigned long long ticket) {
+    if (!p) return fail(FD_ERR_INVALID, "NULL plan");
+    if (ticket >= p->pipe_next) return fail(FD_ERR_INVALID, "unknown ticket");
+    if (ticket + kPipeSlots < p->pipe_next) return FD_OK;        // its slot was already recycled, hence complete
+    DeviceGuard guard(p->device);
+    fd_plan::PipeSlot& sl = p->pipe[ticket % kPipeSlots];
+    if (sl.busy) {
+        FD_CUDA_OK(cudaEventSynchronize(sl.down));
+        sl.busy = false;
+    }
+    return FD_OK;
+}
+
 int fd_stage_buffer(fd_plan* p, int stage, int which, void** dev_ptr, int* n, int* h, int* w, int* c, int* c_stride) {
     if (!p || stage < 0 || stage >= (int)p->stages.size() || !dev_ptr) return fail(FD_ERR_INVALID, "bad argument");
     Stage& s = p->stages[stage];
@@ -625,6 +687,15 @@ void fd_plan_destroy(fd_plan* p) {
         cudaFree(s.out); cudaFree(s.mid); cudaFree(s.dw_w); cudaFree(s.dw_scale); cudaFree(s.dw_bias);
         cudaFree(s.pw_w); cudaFree(s.pw_w_f32); cudaFree(s.pw_scale); cudaFree(s.pw_bias);
     }
+    for (auto& sl : p->pipe) {
+        cudaFree(sl.x); cudaFree(sl.y);
+        if (sl.up) cudaEventDestroy(sl.up);
+        if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.down) cudaEventDestroy(sl.down);
+    }
+    if (p->pipe_h2d) cudaStreamDestroy(p->pipe_h2d);
+    if (p->pipe_run) cudaStreamDestroy(p->pipe_run);
+    if (p->pipe_d2h) cudaStreamDestroy(p->pipe_d2h);
     cudaFree(p->stage_x); cudaFree(p->stage_y); cudaFree(p->l2_flush);
     delete p;
 }

@@ -146,6 +146,15 @@ class Plan:
     def forward_host(self, x_host, y_host, stream_ptr):
         _lib.check(self.lib.fd_forward_host(self.handle, x_host.data_ptr(), y_host.data_ptr(), stream_ptr))
 
+    def pipeline_submit(self, x_host, y_host):
+        """Asynchronous H2D -> forward -> D2H of one pinned host batch; returns a ticket (fd_pipeline_submit)."""
+        t = ctypes.c_uint64()
+        _lib.check(self.lib.fd_pipeline_submit(self.handle, x_host.data_ptr(), y_host.data_ptr(), ctypes.byref(t)))
+        return t.value
+
+    def pipeline_wait(self, ticket):
+        _lib.check(self.lib.fd_pipeline_wait(self.handle, ticket))
+
     def launches_per_forward(self):
         v = ctypes.c_int()
         _lib.check(self.lib.fd_plan_launches_per_forward(self.handle, ctypes.byref(v)))

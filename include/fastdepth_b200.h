@@ -113,6 +113,14 @@ int fd_forward(fd_plan* plan, const void* x_dev, void* y_dev, void* stream);
  * the stream.  (reference main.py:68 input.cuda() ... main.py:85-98 pred.cpu()) */
 int fd_forward_host(fd_plan* plan, const void* x_host, void* y_host, void* stream);
 
+/* Pipelined end-to-end evaluation from HOST buffers (what the reference's DataLoader(pin_memory) + input.cuda()
+ * + pred.cpu() loop does, main.py:40-41, 68, 85-98, with the copies overlapped): submit() enqueues the upload of
+ * x_host (pinned), the forward and the download into y_host (pinned) on the plan's own three streams and returns
+ * a ticket at once; up to 3 batches are in flight (submit blocks on the oldest when all slots are busy).
+ * wait(ticket) returns when y_host holds that batch's depth maps.  Tickets complete in order. */
+int fd_pipeline_submit(fd_plan* plan, const void* x_host, void* y_host, unsigned long long* ticket);
+int fd_pipeline_wait(fd_plan* plan, unsigned long long ticket);
+
 /* Introspection for stage-parity tests: the NHWC buffer stage `stage` wrote in the last
  * fd_forward (valid until the next one).  c_stride = elements between pixels.
  * which = 0: the stage output (after upsample/skip-add); 1: the depthwise intermediate

@@ -203,3 +203,30 @@ def test_sharded_evaluate_single_gpu():
     assert got['count'] == n
     for k in ('rmse', 'mae', 'delta1', 'absrel', 'lg10'):
         assert got[k] == pytest.approx(want[k], rel=2e-3, abs=1e-4), k
+
+
+def test_pipeline_api_matches_forward():
+    """fd_pipeline_submit / fd_pipeline_wait (host buffers, 3 batches in flight) == fd_forward per batch."""
+    m, sd = make_model(synthetic.STOCK_WIDTHS, torch.float16, (64, 96))
+    from fastdepth_b200.engine import SkipAddEngine
+    eng = SkipAddEngine(m)
+    xs = [synthetic.synthetic_input(4, 64, 96, seed=20 + i).half() for i in range(7)]
+    plan = eng.plan_for(xs[0].cuda())
+    want = []
+    with torch.no_grad():
+        for x in xs:
+            y = torch.empty((4, 1, 64, 96), dtype=torch.float16, device='cuda')
+            plan.forward(x.cuda(), y, torch.cuda.current_stream().cuda_stream)
+            want.append(y.cpu())
+    torch.cuda.synchronize()
+    xh = [x.pin_memory() for x in xs]
+    yh = [torch.empty((4, 1, 64, 96), dtype=torch.float16).pin_memory() for _ in xs]
+    tickets = [plan.pipeline_submit(a, b) for a, b in zip(xh, yh)]
+    assert tickets == list(range(len(xs)))
+    for t in reversed(tickets):
+        plan.pipeline_wait(t)
+    for a, b in zip(yh, want):
+        assert torch.equal(a, b)
+    y2 = torch.empty((4, 1, 64, 96), dtype=torch.float16).pin_memory()
+    plan.forward_host(xh[3], y2, torch.cuda.current_stream().cuda_stream)
+    assert torch.equal(y2, want[3])
