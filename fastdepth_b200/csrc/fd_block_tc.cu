@@ -354,6 +354,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                 //     exactly like a SWIZZLE_128B tensor-map box)
                 //  B: the tile leaves through TMA tensor stores (or, as a fallback, coalesced 16-byte LSU stores)
                 const int nblk = (p.n_cta + 63) >> 6;
+                const float2* aff = s_pw_affine + c.n0;                  // this item's (scale, bias) pairs
                 for (int cb = 0; cb < nblk; ++cb) {
                     uint8_t* stg = smem + stg_grp + (n_stg_g == 2 ? (stg_flip & 1u) * 16384u : 0u);
                     ++stg_flip;
@@ -375,12 +376,13 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                             for (int g = 0; g < 4; ++g) {                 // 8 channels -> one 16-byte chunk
                                 if (g >= 2 && !full) break;
                                 uint32_t pk[4];
+                                float4 af[4];                             // (s0, b0, s1, b1) x 4: independent broadcast loads first
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const float4 af = *reinterpret_cast<const float4*>(s_pw_affine + c.n0 + col0 + g * 8 + 2 * j);   // s0, b0, s1, b1
-                                    pk[j] = MF::pack(affine_act<RELU6>(__uint_as_float(r[g * 8 + 2 * j]), af.x, af.y),
-                                                     affine_act<RELU6>(__uint_as_float(r[g * 8 + 2 * j + 1]), af.z, af.w));
-                                }
+                                for (int j = 0; j < 4; ++j) af[j] = *reinterpret_cast<const float4*>(aff + col0 + g * 8 + 2 * j);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    pk[j] = MF::pack(affine_act<RELU6>(__uint_as_float(r[g * 8 + 2 * j]), af[j].x, af[j].y),
+                                                     affine_act<RELU6>(__uint_as_float(r[g * 8 + 2 * j + 1]), af[j].z, af[j].w));
                                 *reinterpret_cast<uint4*>(row + (((half * 4 + g) ^ (m & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                             }
                         }
