@@ -11,6 +11,7 @@
 
 namespace fd {
 
+extern int g_use_pdl;
 BlockPlanOut block_tc_debug_plan(int ksize, int stride, int h_out, int w_out, int n, int c_in, int c_out, int head);
 
 // ---- error state -----------------------------------------------------------------------
@@ -85,7 +86,7 @@ struct fd_plan {
     std::vector<Stage> stages;
     std::vector<Step> steps;
     bool steps_valid = false;
-    int opt_path = 1, opt_fold_head = 1, opt_graph = 1, opt_tma_epilogue = 1, opt_inplace_skip = 1;
+    int opt_path = 1, opt_fold_head = 1, opt_graph = 1, opt_tma_epilogue = 1, opt_inplace_skip = 1, opt_pdl = 1;
     size_t workspace_bytes = 0;
     // fd_pipeline_*: host batches flow H2D -> forward -> D2H through kPipeSlots device slots on three streams
     struct PipeSlot { void* x = nullptr; void* y = nullptr; cudaEvent_t up = nullptr, done = nullptr, down = nullptr; bool busy = false; };
@@ -270,6 +271,7 @@ static int build_steps(fd_plan* p) {
 }
 
 static int run_steps(fd_plan* p, const void* x, void* y, cudaStream_t st) {
+    g_use_pdl = p->opt_pdl;
     for (auto& s : p->steps) {
         int rc = s.run(st, x, y);
         if (rc != FD_OK) return rc;
@@ -417,6 +419,7 @@ static int* option_slot(fd_plan* p, const char* name) {
     if (!strcmp(name, "graph")) return &p->opt_graph;
     if (!strcmp(name, "tma_epilogue")) return &p->opt_tma_epilogue;
     if (!strcmp(name, "inplace_skip")) return &p->opt_inplace_skip;
+    if (!strcmp(name, "pdl")) return &p->opt_pdl;
     return nullptr;
 }
 

@@ -157,6 +157,8 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         s_pw_affine[i] = p.pw_affine[i];
         if (p.head) s_head_w[i] = p.head_w[i];
     }
+    pdl_launch_dependents();                       // the next kernel may begin its own prologue
+    pdl_wait_prior_grid();                         // everything below reads what the previous kernel wrote
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -278,6 +280,11 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                 for (int i = 0; i < KS * KS; ++i) wv[i] = *reinterpret_cast<const uint32_t*>(prm + i * 128 + lane * 4);
                 const float2 sc = *reinterpret_cast<const float2*>(prm + KS * KS * 128 + lane * 8);
                 const float2 bi = *reinterpret_cast<const float2*>(prm + KS * KS * 128 + 256 + lane * 8);
+                // the A stage is normally free long before (deep ring): take it now so that every output row can be
+                // published the moment its last input row has been consumed -- the stores then drain during the math and
+                // the proxy fence at the end (a MEMBAR.ALL.CTA, ~36 cycles per store still in flight) finds few pending
+                mbar_wait(smem_u32(&bars->a_empty[sa]), pha ^ 1u);
+                uint8_t* a_s = smem + a_off + sa * TC_A_STAGE_BYTES;
                 float acc[4][4][2];
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
@@ -297,24 +304,21 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
 #pragma unroll
                             for (int kx = 0; kx < KS; ++kx)
                                 MF::fma2(acc[oy][ox][0], acc[oy][ox][1], row[ox * STRIDE + kx], wv[ky * KS + kx]);
+                        if (ky == KS - 1) {                               // output row oy is complete: BN, act, pack, publish
+#pragma unroll
+                            for (int ox = 0; ox < 4; ++ox) {
+                                const int m = (ni * TH + br * 4 + oy) * TW + bc * 4 + ox;
+                                const float lo = affine_act<RELU6>(acc[oy][ox][0], sc.x, bi.x);
+                                const float hi = affine_act<RELU6>(acc[oy][ox][1], sc.y, bi.y);
+                                *reinterpret_cast<uint32_t*>(a_s + m * 128 + (((lane >> 2) ^ (m & 7)) << 4) + ((lane & 3) << 2)) = MF::pack(lo, hi);
+                            }
+                        }
                     }
                 }
+                if (tracer) TC_TRACE(2, tr);
                 // the input stage can be refilled as soon as every warp has read it
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bars->in_empty[s]));
-
-                if (tracer) TC_TRACE(2, tr);
-                mbar_wait(smem_u32(&bars->a_empty[sa]), pha ^ 1u);
-                uint8_t* a_s = smem + a_off + sa * TC_A_STAGE_BYTES;
-#pragma unroll
-                for (int oy = 0; oy < 4; ++oy)
-#pragma unroll
-                    for (int ox = 0; ox < 4; ++ox) {
-                        const int m = (ni * TH + br * 4 + oy) * TW + bc * 4 + ox;
-                        const float lo = affine_act<RELU6>(acc[oy][ox][0], sc.x, bi.x);
-                        const float hi = affine_act<RELU6>(acc[oy][ox][1], sc.y, bi.y);
-                        *reinterpret_cast<uint32_t*>(a_s + m * 128 + (((lane >> 2) ^ (m & 7)) << 4) + ((lane & 3) << 2)) = MF::pack(lo, hi);
-                    }
                 fence_proxy_async();             // generic-proxy writes -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bars->a_full[sa]));
@@ -516,6 +520,8 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
 // ----------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------
+int g_use_pdl = 1;
+
 PFN_encodeTiled get_tensor_map_encoder() {
     static PFN_encodeTiled fn = nullptr;
     if (fn) return fn;
@@ -560,7 +566,13 @@ static int launch_inst2(BlockTcPlan* bp, cudaStream_t st) {
         FD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    kern<<<bp->grid, TC_THREADS, bp->smem_bytes, st>>>(bp->tm_in, bp->tm_w, bp->tm_o[0], bp->tm_o[1], bp->tm_o[2], bp->tm_o[3], bp->p);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = bp->grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = bp->smem_bytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
+    FD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, bp->tm_in, bp->tm_w, bp->tm_o[0], bp->tm_o[1], bp->tm_o[2], bp->tm_o[3], bp->p));
     FD_CUDA_OK(cudaGetLastError());
     return FD_OK;
 }

@@ -73,6 +73,8 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     if (warp == ST_WARP_TMA && lane == 0) { tma_prefetch_desc(&tm_in); tma_prefetch_desc(&tm_w); }
     for (int i = threadIdx.x; i < p.n_pad; i += ST_THREADS) s_affine[i] = p.affine[i];
     // the K = 32..63 half of every A row is never read (only two K=16 steps are issued), no need to clear it
+    pdl_launch_dependents();                       // the next kernel may begin its own prologue
+    pdl_wait_prior_grid();                         // everything below reads what the previous kernel wrote
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -323,13 +325,19 @@ int stem_tc_launch(StemTcPlan* sp, const void* x, cudaStream_t st) {
         int rc = encode_input_map(sp, x);
         if (rc) return rc;
     }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = sp->grid; cfg.blockDim = dim3(ST_THREADS); cfg.dynamicSmemBytes = sp->smem_bytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
     static bool attr_done[2] = {false, false};
     if (sp->dtype == FD_F16) {
         if (!attr_done[0]) { FD_CUDA_OK(cudaFuncSetAttribute(stem_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done[0] = true; }
-        stem_tc_kernel<__half><<<sp->grid, ST_THREADS, sp->smem_bytes, st>>>(sp->tm_in, sp->tm_w, sp->p);
+        FD_CUDA_OK(cudaLaunchKernelEx(&cfg, stem_tc_kernel<__half>, sp->tm_in, sp->tm_w, sp->p));
     } else {
         if (!attr_done[1]) { FD_CUDA_OK(cudaFuncSetAttribute(stem_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done[1] = true; }
-        stem_tc_kernel<__nv_bfloat16><<<sp->grid, ST_THREADS, sp->smem_bytes, st>>>(sp->tm_in, sp->tm_w, sp->p);
+        FD_CUDA_OK(cudaLaunchKernelEx(&cfg, stem_tc_kernel<__nv_bfloat16>, sp->tm_in, sp->tm_w, sp->p));
     }
     FD_CUDA_OK(cudaGetLastError());
     return FD_OK;

@@ -179,6 +179,11 @@ template <> struct MixFma<__nv_bfloat16> {
     static constexpr uint32_t kUmmaFormat = 1;   // BF16
 };
 
+// programmatic dependent launch: let the next kernel of the stream start its prologue on SMs this grid has already left,
+// and make this kernel's first global access wait for the previous grid's memory to be visible
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // stage index + phase parity of an mbarrier ring, advanced without div/mod
 struct Ring {
     uint32_t s = 0, ph = 0;
@@ -198,6 +203,7 @@ __device__ __forceinline__ float affine_act(float acc, float s, float b) {
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-PFN_encodeTiled get_tensor_map_encoder();     // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (no libcuda link)
+PFN_encodeTiled get_tensor_map_encoder();
+extern int g_use_pdl;                          // set from fd_plan option "pdl" before launching     // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (no libcuda link)
 
 }  // namespace fd

@@ -100,7 +100,9 @@ int fd_plan_set_stage_weights(fd_plan* plan, int stage,
  *   "tma_epilogue" 1 = fused blocks write their output tiles with TMA tensor stores  [default 1]
  *   "inplace_skip" 1 = decoder blocks ADD their upsampled output into the skip tensor in place
  *                (TMA reduce-add); the skip source's stage buffer then holds the decoder output
- *                after fd_forward (set 0 for stage-by-stage inspection)  [default 1]            */
+ *                after fd_forward (set 0 for stage-by-stage inspection)  [default 1]
+ *   "pdl"        1 = tensor-core kernels are launched with programmatic dependent launch so that each
+ *                kernel's prologue overlaps the previous kernel's tail  [default 1]            */
 int fd_plan_set_option(fd_plan* plan, const char* name, int value);
 int fd_plan_get_option(fd_plan* plan, const char* name, int* value);
 
