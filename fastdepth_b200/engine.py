@@ -22,8 +22,9 @@ class SkipAddEngine:
     def _weights_signature(self):
         """Cheap per-call check that catches .cuda()/.half()/.to()/load_state_dict().
         In-place edits of a single layer need an explicit ``refresh()``."""
-        w0 = self.module.conv0[0].weight
-        bn = self.module.decode_conv6[1]
+        enc, _, head, _, _ = _plan._blocks_of(self.module)
+        w0 = enc[0][0].weight
+        bn = head[1]
         return (w0.data_ptr(), w0.dtype, w0._version, bn.running_var.data_ptr(), bn.running_var._version,
                 bn.weight._version)
 
@@ -47,11 +48,11 @@ class SkipAddEngine:
             raise RuntimeError("fastdepth_b200 is inference-only: call model.eval() first "
                                "(BatchNorm is folded from running statistics, reference main.py:65)")
         if not x.is_cuda:
-            raise RuntimeError("fastdepth_b200: MobileNetSkipAdd.forward needs a CUDA tensor; "
+            raise RuntimeError("fastdepth_b200: the accelerated forward needs a CUDA tensor; "
                                "there is no CPU fallback (use models.MobileNet for CPU plumbing)")
         if x.dim() != 4 or x.shape[1] != 3:
             raise RuntimeError("expected input [N,3,H,W], got %s" % (tuple(x.shape),))
-        wdtype = m.conv0[0].weight.dtype
+        wdtype = _plan._blocks_of(m)[0][0][0].weight.dtype
         if x.dtype != wdtype:
             raise RuntimeError("Input type (%s) and weight type (%s) should be the same" % (x.dtype, wdtype))
         if x.dtype not in _SUPPORTED:

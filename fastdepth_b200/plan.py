@@ -52,25 +52,54 @@ def _sq(v):
     return int(v[0]) if isinstance(v, (tuple, list)) else int(v)
 
 
-def describe(module):
-    """Walk conv0..conv13, decode_conv1..6 and return (stage descs, per-stage weight tuples).
+def _blocks_of(module):
+    """(encoder blocks[14], decoder blocks[5], head, skips?) for the two module shapes on the hot path:
+    ``MobileNetSkipAdd`` (children conv0..13, decode_conv1..6; reference models.py:674-698) and
+    ``MobileNet`` with the depthwise NNConv decoder (children mobilenet[0..13], decoder.conv1..6; reference
+    models.py:229-244, 441-455)."""
+    if hasattr(module, 'conv0') and hasattr(module, 'decode_conv6'):
+        enc = [getattr(module, 'conv%d' % i) for i in range(14)]
+        dec = [getattr(module, 'decode_conv%d' % j) for j in range(1, 6)]
+        names = ['conv%d' % i for i in range(14)] + ['decode_conv%d' % j for j in range(1, 7)]
+        return enc, dec, module.decode_conv6, True, names
+    if hasattr(module, 'mobilenet') and hasattr(module, 'decoder'):
+        enc = [module.mobilenet[i] for i in range(14)]
+        dec = [getattr(module.decoder, 'conv%d' % j) for j in range(1, 6)]
+        names = ['mobilenet.%d' % i for i in range(14)] + ['decoder.conv%d' % j for j in range(1, 7)]
+        return enc, dec, module.decoder.conv6, False, names
+    raise RuntimeError('unsupported module for the fastdepth_b200 hot path: %s' % type(module).__name__)
 
-    Mirrors the dispatch of reference models.py:706-732: 14 encoder blocks with skips saved
-    after blocks 1/3/5, five decoder blocks each followed by nearest x2 (+skip for 2/3/4), head."""
-    descs, weights, names = [], [], []
-    conv0 = module.conv0
+
+def supports(module):
+    """True if ``describe`` can express the module: depthwise-separable decoder blocks of two Sequentials."""
+    try:
+        enc, dec, head, _, _ = _blocks_of(module)
+        return all(isinstance(b, nn.Sequential) and len(b) == 2 and isinstance(b[0], nn.Sequential) and
+                   b[0][0].groups == b[0][0].in_channels for b in dec)
+    except Exception:
+        return False
+
+
+def describe(module):
+    """Walk the 14 encoder blocks, 5 decoder blocks and the head and return (stage descs, per-stage weight
+    tuples, stage names).
+
+    Mirrors the dispatch of reference models.py:706-732 (SkipAdd: skips saved after encoder blocks 1/3/5 and added
+    after decoder stages 4/3/2) and models.py:253-270, 457-460 (MobileNet + NNConv: no skips)."""
+    enc, dec, hd, with_skips, names = _blocks_of(module)
+    descs, weights = [], []
+    conv0 = enc[0]
     c, bn, act = conv0[0], conv0[1], conv0[2]
     descs.append(dict(kind=_lib.FD_STAGE_STEM, c_in=c.weight.shape[1], c_out=c.weight.shape[0],
                       ksize=_sq(c.kernel_size), stride=_sq(c.stride), act=_act_of(act), upsample=0, skip_src=-1))
     s, b = fold_bn(bn)
     weights.append((None, None, None, _w(c), s, b))
-    names.append('conv0')
     stage_of_encoder = {0: 0}
     for i in range(1, 14):
-        blk = getattr(module, 'conv%d' % i)
+        blk = enc[i]
         dw, bn1, a1, pw, bn2, a2 = blk[0], blk[1], blk[2], blk[3], blk[4], blk[5]
         if _act_of(a1) != _act_of(a2):
-            raise RuntimeError('conv%d: mixed activations are not supported' % i)
+            raise RuntimeError('encoder block %d: mixed activations are not supported' % i)
         descs.append(dict(kind=_lib.FD_STAGE_DWPW, c_in=dw.weight.shape[0], c_out=pw.weight.shape[0],
                           ksize=_sq(dw.kernel_size), stride=_sq(dw.stride), act=_act_of(a1), upsample=0, skip_src=-1))
         s1, b1 = fold_bn(bn1)
@@ -78,25 +107,21 @@ def describe(module):
         weights.append((_w(dw).reshape(dw.weight.shape[0], -1), s1, b1,
                         _w(pw).reshape(pw.weight.shape[0], pw.weight.shape[1]), s2, b2))
         stage_of_encoder[i] = len(descs) - 1
-        names.append('conv%d' % i)
     for j in range(1, 6):
-        blk = getattr(module, 'decode_conv%d' % j)
+        blk = dec[j - 1]
         (dw, bn1, a1), (pw, bn2, a2) = (blk[0][0], blk[0][1], blk[0][2]), (blk[1][0], blk[1][1], blk[1][2])
-        skip = stage_of_encoder[SKIP_FOR_DECODE[j]] if j in SKIP_FOR_DECODE else -1
+        skip = stage_of_encoder[SKIP_FOR_DECODE[j]] if (with_skips and j in SKIP_FOR_DECODE) else -1
         descs.append(dict(kind=_lib.FD_STAGE_DWPW, c_in=dw.weight.shape[0], c_out=pw.weight.shape[0],
                           ksize=_sq(dw.kernel_size), stride=1, act=_act_of(a1), upsample=1, skip_src=skip))
         s1, b1 = fold_bn(bn1)
         s2, b2 = fold_bn(bn2)
         weights.append((_w(dw).reshape(dw.weight.shape[0], -1), s1, b1,
                         _w(pw).reshape(pw.weight.shape[0], pw.weight.shape[1]), s2, b2))
-        names.append('decode_conv%d' % j)
-    hd = module.decode_conv6
     c, bn, act = hd[0], hd[1], hd[2]
     descs.append(dict(kind=_lib.FD_STAGE_HEAD, c_in=c.weight.shape[1], c_out=1, ksize=1, stride=1,
                       act=_act_of(act), upsample=0, skip_src=-1))
     s, b = fold_bn(bn)
     weights.append((None, None, None, _w(c).reshape(1, -1), s, b))
-    names.append('decode_conv6')
     return descs, weights, names
 
 

@@ -134,3 +134,17 @@ def synthetic_target(pred, seed=1):
     rng = np.random.Generator(np.random.PCG64(seed))
     noise = torch.from_numpy(rng.standard_normal(tuple(pred.shape)).astype(np.float32))
     return (pred.float().cpu() * (1.0 + 0.1 * noise)).clamp_min(1e-3)
+
+
+def to_mobilenet_keys(sd):
+    """Rename a MobileNetSkipAdd-schema state_dict to the ``models.MobileNet(decoder='nnconv5dw')`` schema
+    (``conv<i>.*`` -> ``mobilenet.<i>.*``, ``decode_conv<j>.*`` -> ``decoder.conv<j>.*``)."""
+    out = {}
+    for k, v in sd.items():
+        if k.startswith('decode_conv'):
+            j, rest = k[len('decode_conv'):].split('.', 1)
+            out['decoder.conv%s.%s' % (j, rest)] = v
+        else:
+            i, rest = k[len('conv'):].split('.', 1)
+            out['mobilenet.%s.%s' % (i, rest)] = v
+    return out

@@ -17,8 +17,10 @@ What is here and what is not:
   ``fastdepth_b200`` plan and makes one C-ABI call.  There is NO CPU fallback
   and NO PyTorch-eager fallback: a missing extension or a CPU tensor raises.
 * ``MobileNet`` + ``NNConv``  -- BASELINE config 1 plumbing
-  ("MobileNet-NNConv5", dense or depthwise decoder, no skips).  Plain
-  PyTorch, runs on CPU; not a kernel target.
+  ("MobileNet-NNConv5", dense or depthwise decoder, no skips).  On CPU, and with
+  the dense 5x5 decoder everywhere, it is plain PyTorch exactly like the reference;
+  a CUDA tensor through the depthwise decoder ("MobileNet-NNConv5(depthwise)",
+  SURVEY.md section 8f row 2) takes the same fused kernels as MobileNetSkipAdd.
 * every other decoder/encoder family of the reference (DeConv, UpConv, UpProj,
   BLConv, ShuffleConv, ResNet*, MobileNetSkipConcat) is out of scope of this
   tier; ``choose_decoder`` names them in its error.
@@ -159,7 +161,24 @@ class MobileNet(nn.Module):
         self.mobilenet = nn.Sequential(*blocks)
         self.decoder = choose_decoder(decoder)
 
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop('_fd_engine', None)
+        return state
+
     def forward(self, x):
+        """CPU tensors (BASELINE config 1 plumbing) and the dense 5x5 decoder run on stock PyTorch, exactly like the
+        reference (models.py:457-460).  A CUDA tensor through the depthwise NNConv decoder ("MobileNet-NNConv5(dw)",
+        reference README.md:37) takes the same fused sm_100a path as MobileNetSkipAdd, just without skips."""
+        if x.is_cuda and not self.training:
+            from fastdepth_b200 import plan as _plan
+            if _plan.supports(self):
+                engine = self.__dict__.get('_fd_engine')
+                if engine is None:
+                    from fastdepth_b200.engine import SkipAddEngine
+                    engine = SkipAddEngine(self)
+                    self.__dict__['_fd_engine'] = engine
+                return engine(x)
         return self.decoder(self.mobilenet(x))
 
 

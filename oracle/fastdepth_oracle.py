@@ -122,6 +122,40 @@ def skipadd_forward(sd, x, dtype=torch.float32, stages=None):
     return x
 
 
+def to_skipadd_keys(sd):
+    """state_dict of ``models.MobileNet(decoder='nnconv5dw')`` (keys ``mobilenet.<i>.*``, ``decoder.conv<j>.*``,
+    reference models.py:441, 229-244) renamed to the MobileNetSkipAdd schema used by the functions above."""
+    out = {}
+    for k, v in sd.items():
+        if k.startswith('mobilenet.'):
+            i, rest = k[len('mobilenet.'):].split('.', 1)
+            out['conv%s.%s' % (i, rest)] = v
+        elif k.startswith('decoder.conv'):
+            j, rest = k[len('decoder.conv'):].split('.', 1)
+            out['decode_conv%s.%s' % (j, rest)] = v
+    return out
+
+
+@torch.no_grad()
+def nnconv_dw_forward(sd, x, dtype=torch.float32, stages=None):
+    """MobileNet.forward with the depthwise NNConv decoder (reference models.py:457-460 -> 253-270): the same 14
+    encoder blocks, five (depthwise 5x5 + pointwise) blocks each followed by nearest x2, pointwise(32,1) -- no skips.
+    ``sd`` uses the MobileNet key schema."""
+    sk = to_skipadd_keys(sd)
+    x = stem(x.to(dtype), sk, dtype)
+    if stages is not None:
+        stages['mobilenet.0'] = x
+    for i in range(1, 14):
+        x = encoder_pw(encoder_dw(x, sk, i, dtype), sk, i, dtype)
+        if stages is not None:
+            stages['mobilenet.%d' % i] = x
+    for j in range(1, 6):
+        x = upsample2x(decoder_pw(decoder_dw(x, sk, j, dtype), sk, j, dtype))
+        if stages is not None:
+            stages['decoder.conv%d' % j] = x
+    return head(x, sk, dtype)
+
+
 # --------------------------------------------------------------------------------------
 # metrics (reference metrics.py:31-55, 71-95)
 # --------------------------------------------------------------------------------------

@@ -117,6 +117,22 @@ def make_forward_fixture(ref_models, name, widths, n, h, w, wseed=1, xseed=0):
     np.savez_compressed(os.path.join(HERE, name + '.npz'), **fix)
 
 
+def make_nnconv_dw_fixture(ref_models, name, n, h, w, wseed=1, xseed=0):
+    """reference models.MobileNet(decoder='nnconv5dw') (models.py:420-460 with NNConv(5, dw=True), l.229-244,
+    253-270): the SkipAdd topology without skips -- SURVEY.md section 8f row 2."""
+    sd = synthetic.to_mobilenet_keys(synthetic.synthetic_state_dict(synthetic.STOCK_WIDTHS, seed=wseed))
+    m = ref_models.MobileNet('nnconv5dw', (224, 224), pretrained=False)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    x = synthetic.synthetic_input(n, h, w, seed=xseed)
+    with torch.no_grad():
+        y = m(x)
+    print('== %s: out range %.4g..%.4g mean %.4g frac_zero %.3f' % (name, y.min(), y.max(), y.mean(), (y == 0).float().mean()))
+    assert (y == 0).float().mean() < 0.5
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), shape=np.asarray([n, h, w]), wseed=np.asarray(wseed),
+                        xseed=np.asarray(xseed), output=y.numpy())
+
+
 def make_metrics_fixture(ref_metrics):
     """Known answer for metrics.Result.evaluate (reference metrics.py:31-55) on the reference's own
     sample (deploy/data/pred.npy vs depth.npy), subsampled 4x so the fixture stays small, plus a
@@ -164,5 +180,6 @@ if __name__ == '__main__':
     make_forward_fixture(ref_models, 'skipadd_stock_2x64x96', synthetic.STOCK_WIDTHS, 2, 64, 96)
     make_forward_fixture(ref_models, 'skipadd_pruned_2x64x96', synthetic.PRUNED_WIDTHS, 2, 64, 96)
     make_forward_fixture(ref_models, 'skipadd_stock_1x224x224', synthetic.STOCK_WIDTHS, 1, 224, 224)
+    make_nnconv_dw_fixture(ref_models, 'nnconv5dw_stock_2x64x96', 2, 64, 96)
     make_metrics_fixture(ref_metrics)
     print('wrote fixtures to', HERE)

@@ -230,3 +230,25 @@ def test_pipeline_api_matches_forward():
     y2 = torch.empty((4, 1, 64, 96), dtype=torch.float16).pin_memory()
     plan.forward_host(xh[3], y2, torch.cuda.current_stream().cuda_stream)
     assert torch.equal(y2, want[3])
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+def test_mobilenet_nnconv5dw_no_skips(dtype):
+    """models.MobileNet(decoder='nnconv5dw') takes the same fused path (no skips)."""
+    import models
+    fx = np.load(os.path.join(GOLDEN, 'nnconv5dw_stock_2x64x96.npz'))
+    n, h, w = (int(v) for v in fx['shape'])
+    sd = synthetic.to_mobilenet_keys(synthetic.synthetic_state_dict(seed=int(fx['wseed'])))
+    m = models.MobileNet('nnconv5dw', (h, w), pretrained=False)
+    m.load_state_dict(sd)
+    m = m.eval().cuda().to(dtype)
+    x = synthetic.synthetic_input(n, h, w, seed=int(fx['xseed']))
+    with torch.no_grad():
+        y = m(x.cuda().to(dtype))
+    torch.cuda.synchronize()
+    assert '_fd_engine' in m.__dict__                      # really went through the C-ABI, not PyTorch eager
+    assert rel_err(y.float().cpu(), torch.from_numpy(fx['output'])) <= TOL[dtype]
+    # the dense 5x5 decoder is not a kernel target: it stays on stock PyTorch
+    md = models.MobileNet('nnconv5', (h, w), pretrained=False).eval().cuda()
+    with torch.no_grad():
+        assert md(x.cuda()).shape == (n, 1, h, w) and '_fd_engine' not in md.__dict__

@@ -38,6 +38,15 @@ def test_oracle_forward_matches_reference(name):
         assert torch.allclose(got, ref, rtol=3e-4, atol=3e-4), key    # fp32 summation-order drift
 
 
+def test_oracle_nnconv_dw_matches_reference():
+    """MobileNet + NNConv(5, dw) without skips against the live reference's output."""
+    fx = _load('nnconv5dw_stock_2x64x96')
+    n, h, w = (int(v) for v in fx['shape'])
+    sd = synthetic.to_mobilenet_keys(synthetic.synthetic_state_dict(seed=int(fx['wseed'])))
+    y = orc.nnconv_dw_forward(sd, synthetic.synthetic_input(n, h, w, seed=int(fx['xseed'])))
+    assert rel_err(y, torch.from_numpy(fx['output'])) < 1e-4
+
+
 def test_oracle_fp64_agrees_with_fp32():
     sd = synthetic.synthetic_state_dict(seed=3)
     x = synthetic.synthetic_input(1, 32, 64, seed=5)
