@@ -265,6 +265,13 @@ def main():
         s['frac'] = s['gbs'] / hbm_peak
         s['tflops'] = 2 * s['macs'] / (s['ms'] * 1e-3) / 1e12 if s['ms'] > 0 else 0.0
     top = max(steps, key=lambda s: s['ms'])
+    # DRAM traffic of that kernel from the committed `ncu --set full` capture of the same configuration (if any)
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'r01_final_traffic.json')
+    if os.path.exists(tpath) and args.widths == 'stock' and args.dtype == 'fp16' and n == 64 and (h, w) == (224, 224) and args.path == 1:
+        tj = json.load(open(tpath))['stages'].get(top['stage_name'])
+        if tj:
+            traffic = (tj['dram_read_mb'] + tj['dram_write_mb']) * 1e6
     sum_ms = sum(s['ms'] for s in steps)
     alg_total = sum(s['alg_bytes'] for s in steps)
 
@@ -306,7 +313,7 @@ def main():
         'launches_per_step': plan.launches_per_forward(),
         'clocks': clocks,
         'roofline': {'bound': 'hbm', 'achieved': top['gbs'], 'peak': hbm_peak, 'unit': 'GB/s', 'frac': top['frac'],
-                     'traffic': None, 'kernel': top['kernel'], 'stage': top['stage_name'], 'peak_source': peak_src,
+                     'traffic': traffic, 'kernel': top['kernel'], 'stage': top['stage_name'], 'peak_source': peak_src,
                      'kernel_ms': top['ms'], 'share_of_step': top['ms'] / sum_ms,
                      'whole_step': {'alg_bytes': alg_total, 'gbs_at_value': alg_total / (ms_total / args.steps * 1e-3) / 1e9,
                                     'frac_at_value': alg_total / (ms_total / args.steps * 1e-3) / 1e9 / hbm_peak}},
