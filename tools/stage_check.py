@@ -1,5 +1,5 @@
 import sys, torch, numpy as np
-sys.path.insert(0,'/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import models
 from fastdepth_b200 import synthetic
 from fastdepth_b200.engine import SkipAddEngine
