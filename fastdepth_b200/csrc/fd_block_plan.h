@@ -31,16 +31,30 @@ inline BlockPlanOut plan_block(const BlockPlanIn& q) {
     const int IH = (TH - 1) * q.stride + q.ksize, IW = (TW - 1) * q.stride + q.ksize;
     p.kblocks = (q.c_in + kPlanKblk - 1) / kPlanKblk;
     p.cin_pad = p.kblocks * kPlanKblk;
-    // split the output channels into items until there are enough items for the 148 SMs (each item recomputes the
-    // cheap depthwise half) and the per-item accumulator pair fits the 512 TMEM columns
+    // Split the output channels into items (each item recomputes the depthwise half for its 128 pixels, so splitting is
+    // not free).  Candidates: n_cta <= 256 (two TMEM accumulators), multiples of 64 when there is more than one split
+    // (the epilogue moves whole [128 px][64 ch] tiles and must not touch a neighbouring split's columns).  Pick the
+    // candidate with the smallest modelled kernel time: rounds over the 148 SMs x (K-blocks x max(depthwise, MMA) cycles)
+    // + the last item's exposed epilogue.  The per-K-block cycle counts are the measured ones (profiles/r01_trace_*).
     const int cout_pad = (q.c_out + 15) / 16 * 16;
     int splits = 1;
-    while ((cout_pad + splits - 1) / splits > 256 || (q.n_tiles * splits < 148 && (cout_pad / (splits * 2)) >= 64 && !q.head)) splits *= 2;
-    p.n_cta = ((cout_pad + splits - 1) / splits + 15) / 16 * 16;
-    // with several splits every item's channel range must end on a 64-channel boundary: the epilogue moves whole
-    // [128 px][64 ch] tiles and must not touch a neighbouring split's columns
-    if (splits > 1) p.n_cta = (p.n_cta + 63) / 64 * 64;
-    splits = (cout_pad + p.n_cta - 1) / p.n_cta;
+    {
+        const long dw_c = q.ksize == 5 ? 2100 : (q.stride == 2 ? 1200 : 1000);
+        long best_t = -1;
+        for (int n_cta = 256; n_cta >= 64; n_cta -= 64) {
+            int sp = (cout_pad + n_cta - 1) / n_cta, nc = n_cta;
+            if (sp == 1) nc = cout_pad;                              // a single split needs no 64-alignment
+            if (sp == 1 && cout_pad > 256) continue;
+            if (q.head && sp > 1) continue;
+            const long items = (long)q.n_tiles * sp;
+            const long rounds = (items + 147) / 148;
+            const long mma_c = 2L * nc;                              // 128 x nc x 64 MACs at 4096 MAC/clk
+            const long kb_c = (dw_c > mma_c ? dw_c : mma_c) + 100;
+            const long t = rounds * p.kblocks * kb_c + 45L * nc;
+            if (best_t < 0 || t < best_t) { best_t = t; splits = sp; p.n_cta = nc; }
+        }
+        if (cout_pad <= 64 || q.head) { splits = 1; p.n_cta = cout_pad; }
+    }
     p.splits = splits;
     p.items = q.n_tiles * splits;
     p.cpad_all = p.n_cta * splits;
