@@ -84,7 +84,7 @@ inline BlockPlanOut plan_block(const BlockPlanIn& q) {
                 const int w_all = p.kblocks * nb * bn * 128;
                 const bool can_res = splits == 1 && bn == bn_top && p.kblocks * nb <= kPlanMaxB && w_all <= 64 * 1024;
                 for (int res = can_res ? 1 : 0; res >= 0; --res)
-                    for (int s_b = res ? p.kblocks * nb : 3; s_b >= (res ? p.kblocks * nb : 2); --s_b) {
+                    for (int s_b = res ? p.kblocks * nb : 6; s_b >= (res ? p.kblocks * nb : 2); --s_b) {
                         if (!res && s_b > p.kblocks * nb && s_b > 2) continue;
                         const int left = avail - s_b * bn * 128;
                         if (left < 0) continue;
@@ -92,8 +92,12 @@ inline BlockPlanOut plan_block(const BlockPlanIn& q) {
                         if (s_in > kPlanMaxIn) s_in = kPlanMaxIn;
                         if (s_in < 2 && !(s_in == 1 && p.kblocks == 1 && p.items <= 148)) continue;
                         const int bn_eff = bn < 128 ? bn : 128;
+                        // weight ring depth in K-blocks: below 2 the MMA of K-block k+1 waits for a weight load that could
+                        // only start when the MMA of K-block k had finished (measured: conv7 lost a third of its time there)
+                        const int b_ahead2 = res ? 4 : (2 * s_b / nb > 4 ? 4 : 2 * s_b / nb);      // in half K-blocks, capped at 2 K-blocks
                         long score = (long)bn_eff * 100 + (bn >= 256 ? 500 : 0) + (s_in > 4 ? 4 : s_in) * 2500 +
-                                     s_a * (p.kblocks <= 2 ? 1500 : 400) + groups * 2500 + n_stg * 300 + (res ? 1000 : 0) + s_b * 100;
+                                     s_a * (p.kblocks <= 2 ? 1500 : 400) + groups * 2500 + n_stg * 300 + (res ? 1000 : 0) +
+                                     b_ahead2 * 1800;
                         if (bn < 64 && bn < bn_top) score -= 20000;          // narrow MMAs are a last resort
                         if (score > best) {
                             found = true; best = score;
