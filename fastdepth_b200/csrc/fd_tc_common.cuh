@@ -21,14 +21,17 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Blocking wait with a suspend-time hint: the thread is parked by the hardware (no issue slots burnt) until the phase
+// completes or the hint (ns) expires, instead of spinning on short default time-outs -- in the ncu instruction mix of the
+// hint-less version 40 % of all issued warp-instructions of decode_conv5 were TRYWAIT/BRA/YIELD of waiting warps.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra WAIT_DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+        "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity), "r"(1000000u) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
