@@ -135,6 +135,11 @@ def run_reference(args, rank):
         return
     widths, sd = build_sd(args.widths)
     h, w = args.hw
+    # torchrun exports OMP_NUM_THREADS=1 for every worker; the reference arm is meant to use all host threads it can
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     cores = torch.get_num_threads()
     rate, batch, steps, per = cpu_forward_rate(sd, h, w, budget_s=0, min_steps=max(1, args.steps), warmup=max(1, args.warmup))
     line = {
@@ -288,7 +293,11 @@ def main():
     m_ref, _ = orc.average_per_image(want.numpy(), tgt.numpy())
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+        except Exception:
+            pass
         rate, cb, csteps, per = cpu_forward_rate(sd, h, w, budget_s=15.0, min_steps=3, warmup=1)
         cpu = {'value': rate, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
                'sample': '%d forwards of batch %d at %dx%d, fp32 torch CPU (oracle port of reference models.py:706-732), '
