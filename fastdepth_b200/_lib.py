@@ -17,7 +17,7 @@ FD_ACT_RELU, FD_ACT_RELU6 = 0, 1
 class StageDesc(ctypes.Structure):
     """fd_stage_desc"""
     _fields_ = [(n, ctypes.c_int32) for n in
-                ('kind', 'c_in', 'c_out', 'ksize', 'stride', 'act', 'upsample', 'skip_src')]
+                ('kind', 'c_in', 'c_out', 'ksize', 'stride', 'act', 'upsample', 'skip_src', 'skip_mode')]
 
 
 _c_int_p = ctypes.POINTER(ctypes.c_int)
@@ -72,7 +72,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.fd_abi_version() != 1:
+    if lib.fd_abi_version() != 2:
         raise RuntimeError('fastdepth_b200: ABI version mismatch')
     _lib = lib
     return lib

@@ -28,7 +28,7 @@ int launch_stem(int dtype, const void* x, void* out, const float* w, const float
 int launch_dw(int dtype, const BlockArgs& a, cudaStream_t st);
 int launch_pw(int dtype, const BlockArgs& a, cudaStream_t st);
 int launch_head(int dtype, const void* in, void* out, const float* w, float scale, float bias, long long m_total, int c,
-                int h, int wd, int up, int act, cudaStream_t st);
+                int in_pitch, int h, int wd, int up, int act, cudaStream_t st);
 int launch_metrics(int dtype, const void* pred, const float* target, int n, int hw, double* sums, cudaStream_t st);
 // fused tcgen05 block kernel
 struct BlockTcPlan;   // opaque per-stage state (tensor maps, tile config)
@@ -56,6 +56,10 @@ struct Stage {
     int out_h = 0, out_w = 0;            // spatial size of the stage's output buffer (after upsample)
     void* out = nullptr;                 // NHWC [n,out_h,out_w,c_out]   (STEM/DWPW)
     void* out_eff = nullptr;             // buffer the stage really writes (== a skip source when accumulating in place)
+    void* out_alloc = nullptr;           // what this stage cudaMalloc'ed (out may be a channel slice of another stage's buffer)
+    int out_c = 0;                       // channels the NEXT stage sees (c_out, or c_out + c_skip after a concat)
+    int out_pitch = 0;                   // elements between pixels of `out`
+    int concat_src = -1;                 // >= 0: this stage's output is a channel slice of stage concat_src's wide buffer
     void* mid = nullptr;                 // NHWC [n,h_out,w_out,c_in]     (DWPW, path 0)
     float* dw_w = nullptr;               // [k*k][c_in]
     float* dw_scale = nullptr;
@@ -172,6 +176,9 @@ static int build_steps(fd_plan* p) {
         Stage& s = p->stages[i];
         const void* in = i > 0 ? p->stages[i - 1].out_eff : nullptr;
         s.out_eff = s.out;
+        s.g.in_pitch = i > 0 ? p->stages[i - 1].out_pitch : 0;
+        s.g.out_pitch = s.out_pitch;
+        s.g.skip_pitch = (s.d.skip_src >= 0 && !s.d.skip_mode) ? p->stages[s.d.skip_src].out_pitch : s.out_pitch;
         if (s.d.kind == FD_STAGE_STEM) {
             Step st;
             st.stage = i;
@@ -201,7 +208,7 @@ static int build_steps(fd_plan* p) {
             a.in = in;
             a.mid = s.mid;
             a.out = s.out;
-            a.skip = s.d.skip_src >= 0 ? p->stages[s.d.skip_src].out_eff : nullptr;
+            a.skip = (s.d.skip_src >= 0 && !s.d.skip_mode) ? p->stages[s.d.skip_src].out_eff : nullptr;   // concat: the source wrote its slice itself
             a.dw_w = s.dw_w; a.dw_scale = s.dw_scale; a.dw_bias = s.dw_bias;
             a.pw_w = s.pw_w; a.pw_scale = s.pw_scale; a.pw_bias = s.pw_bias;
             const double px_in = (double)s.g.n * s.g.h_in * s.g.w_in, px_out = (double)s.g.n * s.g.h_out * s.g.w_out;
@@ -258,9 +265,9 @@ static int build_steps(fd_plan* p) {
             st.alg_bytes = ((double)m_total * s.g.c_in + (double)s.g.n * s.g.h_in * s.g.w_in) * es + s.g.c_in * 4.0;
             Stage* sp = &s;
             const int dtype = p->dtype;
-            const int c = s.g.c_in, act = s.g.act;
-            st.run = [sp, in, dtype, m_total, c, hh, ww, up, act](cudaStream_t stream, const void*, void* y) {
-                return launch_head(dtype, in, y, sp->pw_w_f32, sp->head_scale, sp->head_bias, m_total, c, hh, ww, up ? 1 : 0,
+            const int c = s.g.c_in, act = s.g.act, ipitch = s.g.in_pitch;
+            st.run = [sp, in, dtype, m_total, c, ipitch, hh, ww, up, act](cudaStream_t stream, const void*, void* y) {
+                return launch_head(dtype, in, y, sp->pw_w_f32, sp->head_scale, sp->head_bias, m_total, c, ipitch, hh, ww, up ? 1 : 0,
                                    act, stream);
             };
             p->steps.push_back(st);
@@ -339,16 +346,31 @@ int fd_plan_create(const fd_stage_desc* stages, int n_stages, int n, int h, int 
         }
         s.out_h = s.g.h_out * (s.g.upsample ? 2 : 1);
         s.out_w = s.g.w_out * (s.g.upsample ? 2 : 1);
+        s.out_c = d.c_out; s.out_pitch = d.c_out;
         if (d.skip_src >= 0) {
             if (d.kind != FD_STAGE_DWPW || !d.upsample || d.skip_src >= i) { rc = fail(FD_ERR_INVALID, "bad skip_src"); break; }
-            const Stage& src = p->stages[d.skip_src];
-            if (src.out_h != s.out_h || src.out_w != s.out_w || src.g.c_out != d.c_out) {
+            Stage& src = p->stages[d.skip_src];
+            if (src.out_h != s.out_h || src.out_w != s.out_w || (!d.skip_mode && src.g.c_out != d.c_out)) {
                 rc = fail(FD_ERR_INVALID, "stage " + std::to_string(i) + ": skip tensor shape does not match the upsampled output");
                 break; }
+            if (d.skip_mode) {
+                // concatenation (models.py:806-811): one wide NHWC buffer [.., c_out + c_skip]; this stage writes the channel
+                // slice [0, c_out), the skip source is re-pointed to write (and be read by its consumer) in slice [c_out, ..)
+                if (d.skip_mode != 1 || src.concat_src >= 0 || src.d.skip_src >= 0) { rc = fail(FD_ERR_INVALID, "bad skip_mode / skip source"); break; }
+                s.out_c = d.c_out + src.g.c_out; s.out_pitch = s.out_c;
+            }
         }
         if (d.kind != FD_STAGE_HEAD) {
-            rc = dev_alloc(p, &s.out, (size_t)n * s.out_h * s.out_w * d.c_out * es);
+            rc = dev_alloc(p, &s.out, (size_t)n * s.out_h * s.out_w * s.out_pitch * es);
             if (rc) break;
+            s.out_alloc = s.out;
+            if (d.skip_src >= 0 && d.skip_mode) {
+                Stage& src = p->stages[d.skip_src];
+                // the source's own dense buffer stays allocated (freed with the plan) but is no longer used
+                src.out = static_cast<char*>(s.out) + (size_t)d.c_out * es;
+                src.out_pitch = s.out_pitch;
+                src.concat_src = i;
+            }
         }
         if (d.kind == FD_STAGE_DWPW) {
             if ((rc = dev_alloc(p, &s.mid, (size_t)n * s.g.h_out * s.g.w_out * d.c_in * es))) break;
@@ -363,7 +385,7 @@ int fd_plan_create(const fd_stage_desc* stages, int n_stages, int n, int h, int 
         }
         if ((rc = dev_alloc(p, (void**)&s.pw_scale, (size_t)d.c_out * 4))) break;
         if ((rc = dev_alloc(p, (void**)&s.pw_bias, (size_t)d.c_out * 4))) break;
-        ch = d.c_out; hh = s.out_h; ww = s.out_w;
+        ch = s.out_c; hh = s.out_h; ww = s.out_w;
     }
     if (rc == FD_OK && (hh != h || ww != w)) rc = fail(FD_ERR_INVALID, "stage list does not return to the input resolution");
     if (rc != FD_OK) {
@@ -580,7 +602,7 @@ int fd_stage_buffer(fd_plan* p, int stage, int which, void** dev_ptr, int* n, in
     if (h) *h = hh;
     if (w) *w = ww;
     if (c) *c = cc;
-    if (c_stride) *c_stride = cc;
+    if (c_stride) *c_stride = (which == 0 && s.out_pitch > 0) ? s.out_pitch : cc;
     return FD_OK;
 }
 
@@ -687,7 +709,7 @@ void fd_plan_destroy(fd_plan* p) {
     DeviceGuard guard(p->device);
     invalidate(p);
     for (auto& s : p->stages) {
-        cudaFree(s.out); cudaFree(s.mid); cudaFree(s.dw_w); cudaFree(s.dw_scale); cudaFree(s.dw_bias);
+        cudaFree(s.out_alloc ? s.out_alloc : s.out); cudaFree(s.mid); cudaFree(s.dw_w); cudaFree(s.dw_scale); cudaFree(s.dw_bias);
         cudaFree(s.pw_w); cudaFree(s.pw_w_f32); cudaFree(s.pw_scale); cudaFree(s.pw_bias);
     }
     for (auto& sl : p->pipe) {

@@ -70,6 +70,7 @@ struct TcParams {
     int cpad_all;         // n_cta * splits: padded length of the pointwise BN vectors
     int n_stg;            // epilogue staging tiles (16 KB each) in total: epi_groups x (2 or 1)
     int epi_groups;       // 2: two groups of four epilogue warps take alternate items; 1: one group takes all (smem is tight)
+    int out_pitch, skip_pitch;   // elements between pixels of the output / skip tensors (>= c_out: channel slice of a concat buffer)
     int epi_tma;          // 1: staging tiles leave through TMA tensor stores (4 strided views for nearest-x2 upsampling)
     int epi_red;          // 1: ... as element-wise ADD into the skip tensor, which then IS the block's output (in place)
     unsigned long long mg_splits, mg_tx, mg_ty;   // 2^40 / d reciprocals for the item -> tile decode
@@ -439,18 +440,22 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                         if (!(cok && pimg < p.n && poy < p.h_out && pox < p.w_out)) continue;
                         const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
                         if (!p.upsample) {
-                            *reinterpret_cast<uint4*>(outp + (((size_t)pimg * p.h_out + poy) * p.w_out + pox) * p.c_out + c.n0 + ccol) = v;
+                            *reinterpret_cast<uint4*>(outp + (((size_t)pimg * p.h_out + poy) * p.w_out + pox) * p.out_pitch + c.n0 + ccol) = v;
                         } else {
                             const int w2 = 2 * p.w_out;
-                            const size_t off00 = (((size_t)pimg * 2 * p.h_out + 2 * poy) * w2 + 2 * pox) * p.c_out + c.n0 + ccol;
-                            size_t off[4];
+                            const size_t pix00 = ((size_t)pimg * 2 * p.h_out + 2 * poy) * w2 + 2 * pox;
+                            size_t off[4], soff[4];
 #pragma unroll
-                            for (int d = 0; d < 4; ++d) off[d] = off00 + ((size_t)(d >> 1) * w2 + (d & 1)) * p.c_out;
+                            for (int d = 0; d < 4; ++d) {
+                                const size_t pix = pix00 + (size_t)(d >> 1) * w2 + (d & 1);
+                                off[d] = pix * p.out_pitch + c.n0 + ccol;
+                                soff[d] = pix * p.skip_pitch + c.n0 + ccol;
+                            }
                             if (skipp != nullptr) {
                                 // x = interpolate(x) (already rounded to the storage dtype); x = x + skip (models.py:723-729)
                                 uint4 sv[4];
 #pragma unroll
-                                for (int d = 0; d < 4; ++d) sv[d] = __ldg(reinterpret_cast<const uint4*>(skipp + off[d]));
+                                for (int d = 0; d < 4; ++d) sv[d] = __ldg(reinterpret_cast<const uint4*>(skipp + soff[d]));
                                 const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                                 for (int d = 0; d < 4; ++d) {
@@ -689,6 +694,8 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
     p.act = g.act; p.upsample = g.upsample;
     p.head = head_w != nullptr; p.head_act = head_act; p.head_scale = head_scale; p.head_bias = head_bias;
     p.skip = a.skip; p.out = a.out; p.head_out = head_out;
+    p.out_pitch = g.out_pitch > 0 ? g.out_pitch : g.c_out; p.skip_pitch = g.skip_pitch > 0 ? g.skip_pitch : g.c_out;
+    const int in_pitch = g.in_pitch > 0 ? g.in_pitch : g.c_in;
 
     BlockPlanIn pin{};
     pin.ksize = g.ksize; pin.stride = g.stride; pin.tile = bp->tile; pin.c_in = g.c_in; pin.c_out = g.c_out; pin.n_tiles = n_tiles;
@@ -734,7 +741,7 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
     const CUtensorMapDataType dt = dtype == FD_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     {   // input: NHWC viewed as (C, W, H, N); box (64, IW, IH, NI); no swizzle; OOB -> 0 (== zero padding)
         cuuint64_t dims[4] = {(cuuint64_t)g.c_in, (cuuint64_t)g.w_in, (cuuint64_t)g.h_in, (cuuint64_t)g.n};
-        cuuint64_t strides[3] = {(cuuint64_t)g.c_in * es, (cuuint64_t)g.w_in * g.c_in * es, (cuuint64_t)g.h_in * g.w_in * g.c_in * es};
+        cuuint64_t strides[3] = {(cuuint64_t)in_pitch * es, (cuuint64_t)g.w_in * in_pitch * es, (cuuint64_t)g.h_in * g.w_in * in_pitch * es};
         cuuint32_t box[4] = {(cuuint32_t)TC_KBLK, (cuuint32_t)IW, (cuuint32_t)IH, (cuuint32_t)NI};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = encode(&bp->tm_in, dt, 4, const_cast<void*>(a.in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -754,14 +761,14 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
     memset(bp->tm_o, 0, sizeof(bp->tm_o));
     p.epi_tma = (!p.head && tma_epilogue) ? 1 : 0;
     p.epi_red = (p.epi_tma && a.skip != nullptr) ? 1 : 0;
-    if (p.epi_red && a.skip != a.out) { block_tc_destroy(bp); return fail(FD_ERR_STATE, "in-place skip accumulation needs out == skip"); }
+    if (p.epi_red && (a.skip != a.out || p.skip_pitch != p.out_pitch)) { block_tc_destroy(bp); return fail(FD_ERR_STATE, "in-place skip accumulation needs out == skip"); }
     if (p.epi_tma) {
         const int up = g.upsample ? 2 : 1;
-        const cuuint64_t C = (cuuint64_t)g.c_out, W2 = (cuuint64_t)g.w_out * up, H2 = (cuuint64_t)g.h_out * up;
+        const cuuint64_t C = (cuuint64_t)g.c_out, P = (cuuint64_t)p.out_pitch, W2 = (cuuint64_t)g.w_out * up, H2 = (cuuint64_t)g.h_out * up;
         for (int d = 0; d < (g.upsample ? 4 : 1); ++d) {
-            char* base = reinterpret_cast<char*>(a.out) + ((size_t)(d >> 1) * W2 + (d & 1)) * C * es;
+            char* base = reinterpret_cast<char*>(a.out) + ((size_t)(d >> 1) * W2 + (d & 1)) * P * es;
             cuuint64_t dims[4] = {C, (cuuint64_t)g.w_out, (cuuint64_t)g.h_out, (cuuint64_t)g.n};
-            cuuint64_t strides[3] = {up * C * es, up * W2 * C * es, H2 * W2 * C * es};
+            cuuint64_t strides[3] = {up * P * es, up * W2 * P * es, H2 * W2 * P * es};
             cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)NI};
             cuuint32_t estr[4] = {1, 1, 1, 1};
             CUresult r = encode(&bp->tm_o[d], dt, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,

@@ -114,6 +114,9 @@ struct StageGeom {
     int c_in, c_out;
     int ksize, stride, act;
     int upsample;                      // 0/1
+    int in_pitch, out_pitch;           // elements between consecutive pixels of the input / output tensor (>= channels;
+                                       // larger when the tensor is a channel slice of a wider concat buffer)
+    int skip_pitch;                    // same for the skip tensor of an ADD stage
 };
 
 // Launch argument bundle for one fused / unfused block stage.

@@ -22,7 +22,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 stem_kernel(const T* __restrict__ x, T* __restrict__ out, const float* __restrict__ w,
             const float* __restrict__ scale, const float* __restrict__ bias,
-            int n, int h_in, int w_in, int h_out, int w_out, int c_out, int stride, int act) {
+            int n, int h_in, int w_in, int h_out, int w_out, int c_out, int out_pitch, int stride, int act) {
     extern __shared__ float s_w[];                 // [27][c_out] tap-major, then scale, bias
     const int nw = 27 * c_out;
     for (int i = threadIdx.x; i < nw; i += blockDim.x) s_w[i] = w[i];
@@ -66,7 +66,7 @@ stem_kernel(const T* __restrict__ x, T* __restrict__ out, const float* __restric
     float y[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) y[j] = apply_act(fmaf(acc[j], s_scale[g * 8 + j], s_bias[g * 8 + j]), act);
-    T* op = out + (((size_t)img * h_out + oy) * w_out + ox) * c_out + g * 8;
+    T* op = out + (((size_t)img * h_out + oy) * w_out + ox) * out_pitch + g * 8;
     store8<T>(op, y);
 }
 
@@ -77,7 +77,7 @@ template <typename T, int K>
 __global__ void __launch_bounds__(256)
 dw_kernel(const T* __restrict__ in, T* __restrict__ out, const float* __restrict__ w,
           const float* __restrict__ scale, const float* __restrict__ bias,
-          int n, int h_in, int w_in, int h_out, int w_out, int c, int stride, int act) {
+          int n, int h_in, int w_in, int h_out, int w_out, int c, int in_pitch, int stride, int act) {
     const int groups = c >> 3;
     const long long total = (long long)n * h_out * w_out * groups;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -92,7 +92,7 @@ dw_kernel(const T* __restrict__ in, T* __restrict__ out, const float* __restrict
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    const T* base = in + (size_t)img * h_in * w_in * c + g * 8;
+    const T* base = in + (size_t)img * h_in * w_in * in_pitch + g * 8;
 #pragma unroll
     for (int ky = 0; ky < K; ++ky) {
         const int iy = oy * stride - PAD + ky;
@@ -102,7 +102,7 @@ dw_kernel(const T* __restrict__ in, T* __restrict__ out, const float* __restrict
             const int ix = ox * stride - PAD + kx;
             if (ix < 0 || ix >= w_in) continue;
             float v[8], wv[8];
-            load8<T>(base + ((size_t)iy * w_in + ix) * c, v);
+            load8<T>(base + ((size_t)iy * w_in + ix) * in_pitch, v);
             load8<float>(w + (size_t)(ky * K + kx) * c + g * 8, wv);
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[j], wv[j], acc[j]);
@@ -157,7 +157,7 @@ template <typename T>
 __global__ void __launch_bounds__(PW_THREADS)
 pw_kernel(const T* __restrict__ a, const T* __restrict__ wgt, T* __restrict__ out, const T* __restrict__ skip,
           const float* __restrict__ scale, const float* __restrict__ bias,
-          long long m_total, int c_in, int c_out, int h, int w, int upsample, int act) {
+          long long m_total, int c_in, int c_out, int out_pitch, int skip_pitch, int h, int w, int upsample, int act) {
     __shared__ float As[PW_BK][PW_BM + 4];
     __shared__ float Ws[PW_BK][PW_BN + 4];
     const int tid = threadIdx.x;
@@ -206,7 +206,7 @@ pw_kernel(const T* __restrict__ a, const T* __restrict__ wgt, T* __restrict__ ou
 #pragma unroll
         for (int j = 0; j < 4; ++j) y[j] = apply_act(fmaf(acc[i][j], sc[j], bi[j]), act);
         if (!upsample) {
-            store4f<T>(out + (size_t)m * c_out + co, y);
+            store4f<T>(out + (size_t)m * out_pitch + co, y);
         } else {
             const int px = (int)(m % w);
             const long long t = m / w;
@@ -217,11 +217,12 @@ pw_kernel(const T* __restrict__ a, const T* __restrict__ wgt, T* __restrict__ ou
             for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
                 for (int dx = 0; dx < 2; ++dx) {
-                    const size_t o = (((size_t)img * 2 * h + 2 * py + dy) * w2 + 2 * px + dx) * c_out + co;
+                    const size_t pix = ((size_t)img * 2 * h + 2 * py + dy) * w2 + 2 * px + dx;
+                    const size_t o = pix * out_pitch + co;
                     float z[4] = {y[0], y[1], y[2], y[3]};
                     if (skip != nullptr) {
                         float s[4];
-                        load4f<T>(skip + o, s);
+                        load4f<T>(skip + pix * skip_pitch + co, s);
                         // the reference rounds the upsampled tensor to the storage dtype BEFORE the
                         // add (x = F.interpolate(x); x = x + skip, models.py:723-729)
 #pragma unroll
@@ -240,10 +241,10 @@ pw_kernel(const T* __restrict__ a, const T* __restrict__ wgt, T* __restrict__ ou
 template <typename T>
 __global__ void __launch_bounds__(256)
 head_kernel(const T* __restrict__ in, T* __restrict__ out, const float* __restrict__ w, float scale, float bias,
-            long long m_total, int c, int h, int wd, int up, int act) {
+            long long m_total, int c, int in_pitch, int h, int wd, int up, int act) {
     const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= m_total) return;
-    const T* p = in + (size_t)m * c;
+    const T* p = in + (size_t)m * in_pitch;
     float acc = 0.f;
     for (int k = 0; k < c; k += 8) {
         float v[8], wv[8];
@@ -276,7 +277,7 @@ static int launch_stem_t(const void* x, void* out, const float* w, const float* 
     const long long blocks = (total + threads - 1) / threads;
     const size_t smem = (size_t)(27 + 2) * g.c_out * sizeof(float);
     stem_kernel<T><<<(unsigned)blocks, threads, smem, st>>>((const T*)x, (T*)out, w, scale, bias, g.n, g.h_in, g.w_in,
-                                                           g.h_out, g.w_out, g.c_out, g.stride, g.act);
+                                                           g.h_out, g.w_out, g.c_out, g.out_pitch, g.stride, g.act);
     FD_CUDA_OK(cudaGetLastError());
     return FD_OK;
 }
@@ -289,10 +290,10 @@ static int launch_dw_t(const BlockArgs& a, cudaStream_t st) {
     const unsigned blocks = (unsigned)((total + threads - 1) / threads);
     if (g.ksize == 3)
         dw_kernel<T, 3><<<blocks, threads, 0, st>>>((const T*)a.in, (T*)a.mid, a.dw_w, a.dw_scale, a.dw_bias, g.n, g.h_in,
-                                                    g.w_in, g.h_out, g.w_out, g.c_in, g.stride, g.act);
+                                                    g.w_in, g.h_out, g.w_out, g.c_in, g.in_pitch, g.stride, g.act);
     else if (g.ksize == 5)
         dw_kernel<T, 5><<<blocks, threads, 0, st>>>((const T*)a.in, (T*)a.mid, a.dw_w, a.dw_scale, a.dw_bias, g.n, g.h_in,
-                                                    g.w_in, g.h_out, g.w_out, g.c_in, g.stride, g.act);
+                                                    g.w_in, g.h_out, g.w_out, g.c_in, g.in_pitch, g.stride, g.act);
     else
         return fail(FD_ERR_UNSUPPORTED, "depthwise kernel size must be 3 or 5");
     FD_CUDA_OK(cudaGetLastError());
@@ -305,17 +306,17 @@ static int launch_pw_t(const BlockArgs& a, cudaStream_t st) {
     const long long m_total = (long long)g.n * g.h_out * g.w_out;
     dim3 grid((unsigned)((m_total + PW_BM - 1) / PW_BM), (unsigned)((g.c_out + PW_BN - 1) / PW_BN));
     pw_kernel<T><<<grid, PW_THREADS, 0, st>>>((const T*)a.mid, (const T*)a.pw_w, (T*)a.out, (const T*)a.skip, a.pw_scale,
-                                              a.pw_bias, m_total, g.c_in, g.c_out, g.h_out, g.w_out, g.upsample, g.act);
+                                              a.pw_bias, m_total, g.c_in, g.c_out, g.out_pitch, g.skip_pitch, g.h_out, g.w_out, g.upsample, g.act);
     FD_CUDA_OK(cudaGetLastError());
     return FD_OK;
 }
 
 template <typename T>
 static int launch_head_t(const void* in, void* out, const float* w, float scale, float bias, long long m_total, int c,
-                         int h, int wd, int up, int act, cudaStream_t st) {
+                         int in_pitch, int h, int wd, int up, int act, cudaStream_t st) {
     const int threads = 256;
     const unsigned blocks = (unsigned)((m_total + threads - 1) / threads);
-    head_kernel<T><<<blocks, threads, 0, st>>>((const T*)in, (T*)out, w, scale, bias, m_total, c, h, wd, up, act);
+    head_kernel<T><<<blocks, threads, 0, st>>>((const T*)in, (T*)out, w, scale, bias, m_total, c, in_pitch, h, wd, up, act);
     FD_CUDA_OK(cudaGetLastError());
     return FD_OK;
 }
@@ -335,8 +336,8 @@ int launch_stem(int dtype, const void* x, void* out, const float* w, const float
 int launch_dw(int dtype, const BlockArgs& a, cudaStream_t st) { FD_DISPATCH(dtype, launch_dw_t<T>(a, st)); }
 int launch_pw(int dtype, const BlockArgs& a, cudaStream_t st) { FD_DISPATCH(dtype, launch_pw_t<T>(a, st)); }
 int launch_head(int dtype, const void* in, void* out, const float* w, float scale, float bias, long long m_total, int c,
-                int h, int wd, int up, int act, cudaStream_t st) {
-    FD_DISPATCH(dtype, launch_head_t<T>(in, out, w, scale, bias, m_total, c, h, wd, up, act, st));
+                int in_pitch, int h, int wd, int up, int act, cudaStream_t st) {
+    FD_DISPATCH(dtype, launch_head_t<T>(in, out, w, scale, bias, m_total, c, in_pitch, h, wd, up, act, st));
 }
 
 }  // namespace fd

@@ -31,6 +31,7 @@ constexpr int ST_S_IN = 8, ST_S_A = 3;
 
 struct StemParams {
     int n, h_in, w_in, h_out, w_out, c_out, n_pad;   // n_pad: c_out rounded up to 16
+    int out_pitch;                                   // elements between output pixels (>= c_out)
     int tiles_x, tiles_y, items;
     int tmem_cols;
     unsigned long long mg_tx, mg_ty;
@@ -173,7 +174,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
             mbar_wait(smem_u32(&bars->acc_full[racc.s]), racc.ph);
             tc_fence_after();
             const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + racc.s * (uint32_t)p.n_pad;
-            T* o = outp + (((size_t)img * p.h_out + oy) * p.w_out + ox) * p.c_out;
+            T* o = outp + (((size_t)img * p.h_out + oy) * p.w_out + ox) * p.out_pitch;
             for (int b = 0; b < batches; ++b) {
                 uint32_t r[32];
                 const bool full = b * 32 + 32 <= p.n_pad;
@@ -274,6 +275,7 @@ int stem_tc_prepare(int dtype, const StageGeom& g, const float* w27_dev, const f
     memset(&p, 0, sizeof(p));
     p.n = g.n; p.h_in = g.h_in; p.w_in = g.w_in; p.h_out = g.h_out; p.w_out = g.w_out; p.c_out = g.c_out;
     p.n_pad = (g.c_out + 15) / 16 * 16;
+    p.out_pitch = g.out_pitch > 0 ? g.out_pitch : g.c_out;
     p.tiles_x = (g.w_out + ST_TW - 1) / ST_TW; p.tiles_y = (g.h_out + ST_TH - 1) / ST_TH;
     p.items = p.tiles_x * p.tiles_y * g.n;
     p.tmem_cols = 32;

@@ -61,7 +61,11 @@ def _blocks_of(module):
         enc = [getattr(module, 'conv%d' % i) for i in range(14)]
         dec = [getattr(module, 'decode_conv%d' % j) for j in range(1, 6)]
         names = ['conv%d' % i for i in range(14)] + ['decode_conv%d' % j for j in range(1, 7)]
-        return enc, dec, module.decode_conv6, True, names
+        # MobileNetSkipConcat (reference models.py:734-814) has the same children; its decoder blocks 3..5 take the
+        # concatenation [upsampled, skip] -- recognisable by class name (pickles) or by the widened depthwise convs
+        concat = type(module).__name__ == 'MobileNetSkipConcat' or \
+            dec[2][0][0].weight.shape[0] != dec[1][1][0].weight.shape[0]
+        return enc, dec, module.decode_conv6, ('concat' if concat else True), names
     if hasattr(module, 'mobilenet') and hasattr(module, 'decoder'):
         enc = [module.mobilenet[i] for i in range(14)]
         dec = [getattr(module.decoder, 'conv%d' % j) for j in range(1, 6)]
@@ -112,7 +116,8 @@ def describe(module):
         (dw, bn1, a1), (pw, bn2, a2) = (blk[0][0], blk[0][1], blk[0][2]), (blk[1][0], blk[1][1], blk[1][2])
         skip = stage_of_encoder[SKIP_FOR_DECODE[j]] if (with_skips and j in SKIP_FOR_DECODE) else -1
         descs.append(dict(kind=_lib.FD_STAGE_DWPW, c_in=dw.weight.shape[0], c_out=pw.weight.shape[0],
-                          ksize=_sq(dw.kernel_size), stride=1, act=_act_of(a1), upsample=1, skip_src=skip))
+                          ksize=_sq(dw.kernel_size), stride=1, act=_act_of(a1), upsample=1, skip_src=skip,
+                          skip_mode=1 if (with_skips == 'concat' and skip >= 0) else 0))
         s1, b1 = fold_bn(bn1)
         s2, b2 = fold_bn(bn2)
         weights.append((_w(dw).reshape(dw.weight.shape[0], -1), s1, b1,
@@ -224,15 +229,17 @@ class Plan:
                  'epi_tmem_loaded', 'epi_staged', 'epi_barrier', 'epi_store_issued')
         return {n: a[i][a[i] > 0] for i, n in enumerate(names)}
 
-    def stage_tensor(self, stage, which=0):
+    def stage_tensor(self, stage, which=0):  # noqa: C901
         """NHWC view (torch tensor aliasing plan memory) of a stage buffer, for parity tests."""
         ptr = ctypes.c_void_p()
         n, h, w, c, cs = (ctypes.c_int() for _ in range(5))
         _lib.check(self.lib.fd_stage_buffer(self.handle, stage, which, ctypes.byref(ptr), ctypes.byref(n),
                                             ctypes.byref(h), ctypes.byref(w), ctypes.byref(c), ctypes.byref(cs)))
-        numel = n.value * h.value * w.value * cs.value
-        return _alias_device_memory(ptr.value, (n.value, h.value, w.value, c.value), numel, self.dtype,
-                                    self.device_index)
+        # the buffer may be a channel slice of a wider (concat) tensor: pixel pitch cs >= c
+        numel = (n.value * h.value * w.value - 1) * cs.value + c.value
+        flat = _alias_device_memory(ptr.value, (numel,), numel, self.dtype, self.device_index)
+        return flat.as_strided((n.value, h.value, w.value, c.value),
+                               (h.value * w.value * cs.value, w.value * cs.value, cs.value, 1))
 
     def close(self):
         if getattr(self, 'handle', None):

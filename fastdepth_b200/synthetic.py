@@ -42,7 +42,7 @@ BETA = (0.6, 0.25)
 HOT = (0.02, 2.5, 3.5)      # fraction of encoder channels with a large gamma (drives the ReLU6 clamp)
 
 
-def synthetic_state_dict(widths=STOCK_WIDTHS, seed=1, calib_hw=(96, 128)):
+def synthetic_state_dict(widths=STOCK_WIDTHS, seed=1, calib_hw=(96, 128), skip='add'):
     """state_dict (torch fp32 CPU tensors) with the MobileNetSkipAdd key schema
     (SURVEY.md section 8a-a2).
 
@@ -53,7 +53,7 @@ def synthetic_state_dict(widths=STOCK_WIDTHS, seed=1, calib_hw=(96, 128)):
     tolerance is a meaningful bound and not noise.  gamma ~ U(0.25, 0.75) with 2 % "hot" encoder
     channels at U(2.5, 3.5) that drive ~0.1 % of the activations into the ReLU6 clamp;
     beta ~ N(0.6, 0.25) leaves ~10-15 % exact zeros after each ReLU."""
-    key = (tuple(widths[0]), tuple(widths[1]), int(seed), tuple(calib_hw), GAMMA_RANGE, BETA, HOT)
+    key = (tuple(widths[0]), tuple(widths[1]), int(seed), tuple(calib_hw), GAMMA_RANGE, BETA, HOT, skip)
     if key in _CACHE:
         return {k: v.clone() for k, v in _CACHE[key].items()}
     import torch.nn.functional as F
@@ -112,9 +112,13 @@ def synthetic_state_dict(widths=STOCK_WIDTHS, seed=1, calib_hw=(96, 128)):
         x = bn_act(F.conv2d(x, put('decode_conv%d.1.0.weight' % j, unif((co, c, 1, 1), c))), co,
                    'decode_conv%d.1.1' % j, None)
         x = x.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
-        if j in add_after:
-            x = x + keep[add_after[j]]
         c = co
+        if j in add_after:
+            if skip == 'concat':                       # MobileNetSkipConcat (reference models.py:806-811)
+                x = torch.cat((x, keep[add_after[j]]), 1)
+                c = co + keep[add_after[j]].shape[1]
+            else:
+                x = x + keep[add_after[j]]
     bn_act(F.conv2d(x, put('decode_conv6.0.weight', unif((1, c, 1, 1), c).abs())), 1, 'decode_conv6.1', None, last=True)
     # keep the reference's key order (conv.weight first, then BN entries)
     _CACHE[key] = sd

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define FD_ABI_VERSION 1
+#define FD_ABI_VERSION 2
 
 typedef struct fd_plan fd_plan;
 
@@ -69,8 +69,11 @@ typedef struct {
     int32_t stride;      /* stride of the spatial conv (1 or 2)                              */
     int32_t act;         /* fd_act applied after BOTH halves (encoder ReLU6, decoder ReLU)   */
     int32_t upsample;    /* 1: output is 2x nearest-upsampled (F.interpolate, models.py:723) */
-    int32_t skip_src;    /* stage index whose output is ADDED after upsampling
-                            (models.py:724-729), or -1                                       */
+    int32_t skip_src;    /* stage index whose output is combined with this stage's upsampled
+                            output (models.py:724-729 / 806-811), or -1                      */
+    int32_t skip_mode;   /* 0: ADD (MobileNetSkipAdd, models.py:724-729); 1: CONCATENATE along
+                            channels, upsampled output first (MobileNetSkipConcat,
+                            models.py:806-811) -- the next stage then has c_in = c_out + c_skip  */
 } fd_stage_desc;
 
 /* Build a plan for a stage list (always: 1 STEM, k DWPW, 1 HEAD) at a fixed problem size.

@@ -22,8 +22,11 @@ What is here and what is not:
   a CUDA tensor through the depthwise decoder ("MobileNet-NNConv5(depthwise)",
   SURVEY.md section 8f row 2) takes the same fused kernels as MobileNetSkipAdd.
 * every other decoder/encoder family of the reference (DeConv, UpConv, UpProj,
-  BLConv, ShuffleConv, ResNet*, MobileNetSkipConcat) is out of scope of this
-  tier; ``choose_decoder`` names them in its error.
+  BLConv, ShuffleConv, ResNet*) is out of scope of this tier; ``choose_decoder``
+  names them in its error.
+* ``MobileNetSkipConcat``  -- SURVEY.md section 8f row 1: the concat-skip variant
+  (reference models.py:734-814) on the same fused kernels; the concatenation is
+  a channel-slice write into one wide NHWC buffer, never a copy.
 """
 import math
 import os
@@ -237,3 +240,20 @@ class MobileNetSkipAdd(nn.Module):
             engine = SkipAddEngine(self)
             self.__dict__['_fd_engine'] = engine
         return engine(x)
+
+
+class MobileNetSkipConcat(MobileNetSkipAdd):
+    """MobileNet encoder -> NNConv5(depthwise) decoder with CONCATENATED skips.
+
+    Drop-in for reference models.py:734-814: same children (``conv0..conv13``, ``decode_conv1..6``) and ``state_dict``
+    schema; decoder blocks 3, 4, 5 take ``cat(upsampled, skip)`` (512, 256, 128 input channels, reference l.769-777,
+    806-811).  The forward is the same single C-ABI call; ``fastdepth_b200.plan`` marks the three skips as
+    ``skip_mode = 1`` and the kernels write both halves of every concatenation into channel slices of one buffer."""
+
+    def __init__(self, output_size, pretrained=True):
+        super().__init__(output_size, pretrained)
+        kernel_size = 5
+        # (in, out) of decode_conv1..5 with the concatenated skips of conv5 (256), conv3 (128), conv1 (64)
+        for j, (c_in, c_out) in enumerate(((1024, 512), (512, 256), (512, 128), (256, 64), (128, 32)), start=1):
+            setattr(self, 'decode_conv%d' % j, nn.Sequential(depthwise(c_in, kernel_size), pointwise(c_in, c_out)))
+        self.decode_conv6 = pointwise(32, 1)

@@ -122,6 +122,33 @@ def skipadd_forward(sd, x, dtype=torch.float32, stages=None):
     return x
 
 
+@torch.no_grad()
+def skipconcat_forward(sd, x, dtype=torch.float32, stages=None):
+    """MobileNetSkipConcat.forward (reference models.py:789-814): identical to skipadd_forward except that the saved
+    encoder outputs are CONCATENATED after the upsampled decoder output (torch.cat((x, x1), 1), l.806-811)."""
+    x = stem(x.to(dtype), sd, dtype)
+    keep = {}
+    if stages is not None:
+        stages['conv0'] = x
+    for i in range(1, 14):
+        x = encoder_pw(encoder_dw(x, sd, i, dtype), sd, i, dtype)
+        if stages is not None:
+            stages['conv%d' % i] = x
+        if i in (1, 3, 5):
+            keep[i] = x
+    cat_after = {4: 1, 3: 3, 2: 5}
+    for j in range(1, 6):
+        x = upsample2x(decoder_pw(decoder_dw(x, sd, j, dtype), sd, j, dtype))
+        if stages is not None:
+            stages['decode_conv%d' % j] = x            # the block's own slice (before the concatenation)
+        if j in cat_after:
+            x = torch.cat((x, keep[cat_after[j]]), 1)
+    x = head(x, sd, dtype)
+    if stages is not None:
+        stages['decode_conv6'] = x
+    return x
+
+
 def to_skipadd_keys(sd):
     """state_dict of ``models.MobileNet(decoder='nnconv5dw')`` (keys ``mobilenet.<i>.*``, ``decoder.conv<j>.*``,
     reference models.py:441, 229-244) renamed to the MobileNetSkipAdd schema used by the functions above."""

@@ -133,6 +133,21 @@ def make_nnconv_dw_fixture(ref_models, name, n, h, w, wseed=1, xseed=0):
                         xseed=np.asarray(xseed), output=y.numpy())
 
 
+def make_skipconcat_fixture(ref_models, name, n, h, w, wseed=1, xseed=0):
+    """reference models.MobileNetSkipConcat (models.py:734-814) -- SURVEY.md section 8f row 1."""
+    sd = synthetic.synthetic_state_dict(synthetic.STOCK_WIDTHS, seed=wseed, skip='concat')
+    m = ref_models.MobileNetSkipConcat((224, 224), pretrained=False)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    x = synthetic.synthetic_input(n, h, w, seed=xseed)
+    with torch.no_grad():
+        y = m(x)
+    print('== %s: out range %.4g..%.4g mean %.4g frac_zero %.3f' % (name, y.min(), y.max(), y.mean(), (y == 0).float().mean()))
+    assert (y == 0).float().mean() < 0.5
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), shape=np.asarray([n, h, w]), wseed=np.asarray(wseed),
+                        xseed=np.asarray(xseed), output=y.numpy())
+
+
 def make_metrics_fixture(ref_metrics):
     """Known answer for metrics.Result.evaluate (reference metrics.py:31-55) on the reference's own
     sample (deploy/data/pred.npy vs depth.npy), subsampled 4x so the fixture stays small, plus a
@@ -181,5 +196,6 @@ if __name__ == '__main__':
     make_forward_fixture(ref_models, 'skipadd_pruned_2x64x96', synthetic.PRUNED_WIDTHS, 2, 64, 96)
     make_forward_fixture(ref_models, 'skipadd_stock_1x224x224', synthetic.STOCK_WIDTHS, 1, 224, 224)
     make_nnconv_dw_fixture(ref_models, 'nnconv5dw_stock_2x64x96', 2, 64, 96)
+    make_skipconcat_fixture(ref_models, 'skipconcat_stock_2x64x96', 2, 64, 96)
     make_metrics_fixture(ref_metrics)
     print('wrote fixtures to', HERE)

@@ -26,7 +26,7 @@ def test_library_exports_every_symbol(built_lib):
     lib = ctypes.CDLL(built_lib)
     for name in declared_functions():
         assert hasattr(lib, name), name
-    assert _lib.load().fd_abi_version() == 1
+    assert _lib.load().fd_abi_version() == 2
 
 
 def test_no_torch_types_in_signatures():

@@ -252,3 +252,37 @@ def test_mobilenet_nnconv5dw_no_skips(dtype):
     md = models.MobileNet('nnconv5', (h, w), pretrained=False).eval().cuda()
     with torch.no_grad():
         assert md(x.cuda()).shape == (n, 1, h, w) and '_fd_engine' not in md.__dict__
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+@pytest.mark.parametrize('path', [0, 1])
+def test_skipconcat(dtype, path):
+    """MobileNetSkipConcat -- both halves of every concatenation are channel-slice writes
+    into one wide NHWC buffer (TMA stores with a row pitch on path 1, pitched LSU stores on path 0)."""
+    import models
+    orc = oracle()
+    fx = np.load(os.path.join(GOLDEN, 'skipconcat_stock_2x64x96.npz'))
+    n, h, w = (int(v) for v in fx['shape'])
+    sd = synthetic.synthetic_state_dict(seed=int(fx['wseed']), skip='concat')
+    m = models.MobileNetSkipConcat((h, w), pretrained=False)
+    m.load_state_dict(sd)
+    m = m.eval().cuda().to(dtype)
+    x = synthetic.synthetic_input(n, h, w, seed=int(fx['xseed']))
+    y, eng = run(m, x, dtype, path)
+    assert rel_err(y.float().cpu(), torch.from_numpy(fx['output'])) <= TOL[dtype]
+    # stage-wise: the decoder slices and the re-pointed skip sources
+    stages = {}
+    orc.skipconcat_forward(quantised_sd(sd, dtype), x.to(dtype).float(), stages=stages)
+    plan = next(iter(eng.plans.values()))
+    for i, name in enumerate(plan.names[:-2]):
+        got = plan.stage_tensor(i).float().cpu().permute(0, 3, 1, 2)
+        assert got.shape == stages[name].shape, name
+        assert rel_err(got, stages[name]) <= STAGE_TOL[dtype], name
+    # larger problem, many items per CTA
+    x8 = synthetic.synthetic_input(8, 224, 224, seed=3)
+    m2 = models.MobileNetSkipConcat((224, 224), pretrained=False)
+    m2.load_state_dict(sd)
+    m2 = m2.eval().cuda().to(dtype)
+    y8, _ = run(m2, x8, dtype, path)
+    want = orc.skipconcat_forward(quantised_sd(sd, dtype), x8[[0, 7]].to(dtype).float())
+    assert rel_err(y8[[0, 7]].float().cpu(), want) <= TOL[dtype]

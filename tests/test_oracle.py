@@ -47,6 +47,15 @@ def test_oracle_nnconv_dw_matches_reference():
     assert rel_err(y, torch.from_numpy(fx['output'])) < 1e-4
 
 
+def test_oracle_skipconcat_matches_reference():
+    """MobileNetSkipConcat against the live reference's output."""
+    fx = _load('skipconcat_stock_2x64x96')
+    n, h, w = (int(v) for v in fx['shape'])
+    sd = synthetic.synthetic_state_dict(seed=int(fx['wseed']), skip='concat')
+    y = orc.skipconcat_forward(sd, synthetic.synthetic_input(n, h, w, seed=int(fx['xseed'])))
+    assert rel_err(y, torch.from_numpy(fx['output'])) < 1e-4
+
+
 def test_oracle_fp64_agrees_with_fp32():
     sd = synthetic.synthetic_state_dict(seed=3)
     x = synthetic.synthetic_input(1, 32, 64, seed=5)

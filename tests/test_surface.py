@@ -123,3 +123,14 @@ def test_describe_and_bn_folding():
     got = x * torch.from_numpy(s).view(1, -1, 1, 1) + torch.from_numpy(b).view(1, -1, 1, 1)
     assert torch.allclose(got, want, rtol=1e-5, atol=1e-5)
     assert weights[2][0].shape == (56, 9) and weights[2][3].shape == (88, 56)
+
+
+def test_skipconcat_surface():
+    """reference models.py:734-814: same children / key schema as SkipAdd, wider decoder inputs; plan marks concat skips."""
+    m = models.MobileNetSkipConcat((224, 224), pretrained=False)
+    assert list(m.state_dict().keys()) == expected_keys()
+    assert [getattr(m, 'decode_conv%d' % j)[0][0].in_channels for j in range(1, 6)] == [1024, 512, 512, 256, 128]
+    m.load_state_dict(synthetic.synthetic_state_dict(skip='concat'), strict=True)
+    descs, _, _ = plan.describe(m.eval())
+    assert [(d['skip_src'], d.get('skip_mode', 0)) for d in descs[14:19]] == [(-1, 0), (5, 1), (3, 1), (1, 1), (-1, 0)]
+    assert [d['c_in'] for d in descs[14:20]] == [1024, 512, 512, 256, 128, 32]
