@@ -52,6 +52,7 @@ SIGNATURES = {
     'fd_debug_block_plan': (ctypes.c_int, [ctypes.c_int] * 8 + [_c_int_p, ctypes.c_int]),
     'fd_metrics_accumulate': (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp,
                                              ctypes.c_int, _vp]),
+    'fd_nyu_val_gather': (ctypes.c_int, [_vp, _vp, _vp, _vp] + [ctypes.c_int] * 6 + [_vp, _vp, ctypes.c_int, _vp]),
     'fd_plan_destroy': (None, [_vp]),
 }
 

@@ -30,6 +30,8 @@ int launch_pw(int dtype, const BlockArgs& a, cudaStream_t st);
 int launch_head(int dtype, const void* in, void* out, const float* w, float scale, float bias, long long m_total, int c,
                 int in_pitch, int h, int wd, int up, int act, cudaStream_t st);
 int launch_metrics(int dtype, const void* pred, const float* target, int n, int hw, double* sums, cudaStream_t st);
+int launch_nyu_val_gather(int dtype, const uint8_t* rgb, const float* depth, const int* rows, const int* cols, int n, int h_in,
+                          int w_in, int oh, int ow, void* x, float* t, cudaStream_t st);
 // fused tcgen05 block kernel
 struct BlockTcPlan;   // opaque per-stage state (tensor maps, tile config)
 bool block_tc_supported(int dtype, const StageGeom& g, bool head_fused);
@@ -702,6 +704,17 @@ int fd_metrics_accumulate(const void* pred_dev, const float* target_dev, int dty
     DeviceGuard guard(device);
     if (!guard.ok) return fail(FD_ERR_CUDA, "cudaSetDevice failed");
     return launch_metrics(dtype, pred_dev, target_dev, n, hw, sums_dev, (cudaStream_t)stream);
+}
+
+int fd_nyu_val_gather(const uint8_t* rgb_dev, const float* depth_dev, const int* rows_dev, const int* cols_dev, int n, int h_in,
+                      int w_in, int out_h, int out_w, int dtype, void* x_dev, float* target_dev, int device, void* stream) {
+    if (!rgb_dev || !rows_dev || !cols_dev || !x_dev || n < 0 || h_in <= 0 || w_in <= 0 || out_h <= 0 || out_w <= 0)
+        return fail(FD_ERR_INVALID, "bad argument");
+    if ((depth_dev == nullptr) != (target_dev == nullptr)) return fail(FD_ERR_INVALID, "depth and target must come together");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(FD_ERR_CUDA, "cudaSetDevice failed");
+    return launch_nyu_val_gather(dtype, rgb_dev, depth_dev, rows_dev, cols_dev, n, h_in, w_in, out_h, out_w, x_dev, target_dev,
+                                 (cudaStream_t)stream);
 }
 
 void fd_plan_destroy(fd_plan* p) {

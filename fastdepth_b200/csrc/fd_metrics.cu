@@ -83,4 +83,44 @@ int launch_metrics(int dtype, const void* pred, const float* target, int n, int 
     return FD_OK;
 }
 
+// ----------------------------------------------------------------------------------------------
+// NYU val pre-processing as one gather (reference dataloaders/nyu.py:48-59: Resize -> CenterCrop -> Resize, all
+// nearest-neighbour, then rgb / 255; dataloaders/dataloader.py:90-111: HWC -> CHW float).  rows/cols: composed source
+// index tables.  Thread = output pixel; NCHW planes are written coalesced along x.
+// ----------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+nyu_val_gather_kernel(const uint8_t* __restrict__ rgb, const float* __restrict__ depth, const int* __restrict__ rows,
+                      const int* __restrict__ cols, int n, int h_in, int w_in, int oh, int ow, T* __restrict__ x,
+                      float* __restrict__ t) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)n * oh * ow;
+    if (idx >= total) return;
+    const int ox = (int)(idx % ow);
+    const int oy = (int)((idx / ow) % oh);
+    const int img = (int)(idx / ((long long)ow * oh));
+    const size_t src = ((size_t)img * h_in + rows[oy]) * w_in + cols[ox];
+    const size_t plane = (size_t)oh * ow;
+    T* xo = x + (size_t)img * 3 * plane + (size_t)oy * ow + ox;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)      // np.asfarray(rgb, 'float') / 255 (double), then .float()
+        xo[c * plane] = Traits<T>::from_f((float)((double)rgb[src * 3 + c] / 255.0));
+    if (t != nullptr) t[(size_t)img * plane + (size_t)oy * ow + ox] = depth[src];
+}
+
+int launch_nyu_val_gather(int dtype, const uint8_t* rgb, const float* depth, const int* rows, const int* cols, int n, int h_in,
+                          int w_in, int oh, int ow, void* x, float* t, cudaStream_t st) {
+    const long long total = (long long)n * oh * ow;
+    if (total <= 0) return FD_OK;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    switch (dtype) {
+        case FD_F32: nyu_val_gather_kernel<float><<<blocks, 256, 0, st>>>(rgb, depth, rows, cols, n, h_in, w_in, oh, ow, (float*)x, t); break;
+        case FD_F16: nyu_val_gather_kernel<__half><<<blocks, 256, 0, st>>>(rgb, depth, rows, cols, n, h_in, w_in, oh, ow, (__half*)x, t); break;
+        case FD_BF16: nyu_val_gather_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(rgb, depth, rows, cols, n, h_in, w_in, oh, ow, (__nv_bfloat16*)x, t); break;
+        default: return fail(FD_ERR_INVALID, "bad dtype");
+    }
+    FD_CUDA_OK(cudaGetLastError());
+    return FD_OK;
+}
+
 }  // namespace fd

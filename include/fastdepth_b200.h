@@ -170,6 +170,15 @@ int fd_debug_block_plan(int ksize, int stride, int h_out, int w_out, int n, int 
 int fd_metrics_accumulate(const void* pred_dev, const float* target_dev, int dtype, int n, int hw,
                           double* sums_dev, int device, void* stream);
 
+/* NYU-Depth-v2 validation pre-processing as ONE gather launch (reference dataloaders/nyu.py:48-59: Resize(250/480) ->
+ * CenterCrop(228x304) -> Resize(out), all nearest-neighbour, rgb / 255; dataloaders/dataloader.py:90-111: HWC -> CHW).
+ * rgb_dev: [n, h_in, w_in, 3] uint8; depth_dev: [n, h_in, w_in] float or NULL; rows_dev[out_h] / cols_dev[out_w]: the
+ * composed source-index tables (fastdepth_b200/preprocess.py builds them from PIL's own nearest resize);
+ * x_dev: [n, 3, out_h, out_w] of `dtype`; target_dev: [n, 1, out_h, out_w] float or NULL (with depth_dev). */
+int fd_nyu_val_gather(const uint8_t* rgb_dev, const float* depth_dev, const int* rows_dev, const int* cols_dev,
+                      int n, int h_in, int w_in, int out_h, int out_w, int dtype,
+                      void* x_dev, float* target_dev, int device, void* stream);
+
 void fd_plan_destroy(fd_plan* plan);
 
 /* Thread-local message of the last failing call on this thread ("" if none). */

@@ -184,6 +184,38 @@ def nnconv_dw_forward(sd, x, dtype=torch.float32, stages=None):
 
 
 # --------------------------------------------------------------------------------------
+# NYU val pre-processing (reference dataloaders/nyu.py:48-59)  -- PARITY UNPINNED for this function:
+# the reference does the arithmetic with scipy.misc.imresize (dataloaders/transforms.py:337-339), removed in SciPy 1.3
+# and absent here, so the reference's own transform cannot be executed.  scipy 1.2's imresize is restated from its
+# published source: toimage(arr[, mode='F']) -> PIL.Image.resize(size, resample=NEAREST) -> fromimage, with a float
+# `size` meaning "fraction of the current size" (size = (array(im.size) * size).astype(int)).
+# --------------------------------------------------------------------------------------
+def _imresize_nearest(arr, size):
+    from PIL import Image
+    im = Image.fromarray(arr, mode='F') if arr.ndim == 2 else Image.fromarray(arr)
+    if isinstance(size, float):
+        size = (int(im.size[0] * size), int(im.size[1] * size))          # (W, H)
+    else:
+        size = (size[1], size[0])
+    return np.asarray(im.resize(size, resample=Image.NEAREST))
+
+
+def nyu_val_transform(rgb_u8, depth, out_hw=(224, 224), iheight=480.0):
+    """NYUDataset.val_transform (dataloaders/nyu.py:48-59) + ToTensor (dataloaders/dataloader.py:104-109) for ONE
+    sample: rgb_u8 [H,W,3] uint8, depth [H,W] float32 -> (input [3,oh,ow] float32 in [0,1], target [1,oh,ow] float32)."""
+    def chain(a):
+        a = _imresize_nearest(a, 250.0 / iheight)                       # transforms.Resize(250.0 / iheight)
+        h, w = a.shape[0], a.shape[1]
+        i, j = int(round((h - 228) / 2.0)), int(round((w - 304) / 2.0))  # transforms.CenterCrop((228, 304))
+        a = a[i:i + 228, j:j + 304]
+        return _imresize_nearest(np.ascontiguousarray(a), tuple(out_hw))  # transforms.Resize(self.output_size)
+    rgb = np.asarray(chain(rgb_u8), dtype='float') / 255                 # np.asfarray(rgb_np, dtype='float') / 255
+    x = torch.from_numpy(rgb.transpose((2, 0, 1)).copy()).float()
+    t = torch.from_numpy(chain(np.asarray(depth, dtype=np.float32)).copy()).float().unsqueeze(0)
+    return x, t
+
+
+# --------------------------------------------------------------------------------------
 # metrics (reference metrics.py:31-55, 71-95)
 # --------------------------------------------------------------------------------------
 METRIC_NAMES = ('irmse', 'imae', 'mse', 'rmse', 'mae', 'absrel', 'lg10', 'delta1', 'delta2', 'delta3')
