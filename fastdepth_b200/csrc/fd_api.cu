@@ -12,6 +12,7 @@
 namespace fd {
 
 extern int g_use_pdl;
+extern int g_wait_sleep_ns;
 BlockPlanOut block_tc_debug_plan(int ksize, int stride, int h_out, int w_out, int n, int c_in, int c_out, int head);
 
 // ---- error state -----------------------------------------------------------------------
@@ -92,7 +93,7 @@ struct fd_plan {
     std::vector<Stage> stages;
     std::vector<Step> steps;
     bool steps_valid = false;
-    int opt_path = 1, opt_fold_head = 1, opt_graph = 1, opt_tma_epilogue = 1, opt_inplace_skip = 1, opt_pdl = 1;
+    int opt_path = 1, opt_fold_head = 1, opt_graph = 1, opt_tma_epilogue = 1, opt_inplace_skip = 1, opt_pdl = 1, opt_wait_sleep_ns = 100;
     size_t workspace_bytes = 0;
     // fd_pipeline_*: host batches flow H2D -> forward -> D2H through kPipeSlots device slots on three streams
     struct PipeSlot { void* x = nullptr; void* y = nullptr; cudaEvent_t up = nullptr, done = nullptr, down = nullptr; bool busy = false; };
@@ -281,6 +282,7 @@ static int build_steps(fd_plan* p) {
 
 static int run_steps(fd_plan* p, const void* x, void* y, cudaStream_t st) {
     g_use_pdl = p->opt_pdl;
+    g_wait_sleep_ns = p->opt_wait_sleep_ns;
     for (auto& s : p->steps) {
         int rc = s.run(st, x, y);
         if (rc != FD_OK) return rc;
@@ -444,13 +446,16 @@ static int* option_slot(fd_plan* p, const char* name) {
     if (!strcmp(name, "tma_epilogue")) return &p->opt_tma_epilogue;
     if (!strcmp(name, "inplace_skip")) return &p->opt_inplace_skip;
     if (!strcmp(name, "pdl")) return &p->opt_pdl;
+    if (!strcmp(name, "wait_sleep_ns")) return &p->opt_wait_sleep_ns;
     return nullptr;
 }
 
 int fd_plan_set_option(fd_plan* p, const char* name, int value) {
     int* slot = option_slot(p, name);
     if (!slot) return fail(FD_ERR_INVALID, std::string("unknown option: ") + (name ? name : "(null)"));
-    if (value != 0 && value != 1) return fail(FD_ERR_INVALID, "option value must be 0 or 1");
+    const bool is_time = !strcmp(name, "wait_sleep_ns");
+    if (is_time ? (value < 0 || value > 100000) : (value != 0 && value != 1))
+        return fail(FD_ERR_INVALID, is_time ? "wait_sleep_ns must be in [0, 100000]" : "option value must be 0 or 1");
     if (*slot != value) { *slot = value; invalidate(p); }
     return FD_OK;
 }
@@ -695,6 +700,7 @@ int fd_debug_block_plan(int ksize, int stride, int h_out, int w_out, int n, int 
     const int v[16] = {q.ok, q.splits, q.n_cta, q.items, q.kblocks, q.s_in, q.s_a, q.s_b, q.bn, q.nb, q.b_resident, q.epi_groups,
                        q.n_stg, q.smem_bytes, q.tmem_cols, q.in_stage_stride};
     for (int i = 0; i < 16; ++i) out[i] = v[i];
+    if (cap >= 18) { out[16] = q.nacc; out[17] = q.epi_colsplit; }
     return FD_OK;
 }
 

@@ -15,6 +15,8 @@ struct BlockPlanIn {
     int c_in, c_out, n_tiles;    // n_tiles: 128-pixel tiles of the whole problem
     int head;                    // decode_conv6 folded into the epilogue
     int barrier_bytes;           // sizeof(TcBarriers)
+    int max_n_cta;               // 0 = no limit; experiments: cap the output channels per item (FD_TC_MAX_NCTA)
+    int no_colsplit;             // experiments: 1 = epilogue groups take alternate items even when they could share (FD_TC_NO_COLSPLIT)
 };
 struct BlockPlanOut {
     int ok;
@@ -22,51 +24,16 @@ struct BlockPlanOut {
     int in_stage_bytes, dwp_bytes, in_stage_stride;
     int s_in, s_a, s_b, bn, nb, b_resident, b_stage_bytes;
     int epi_groups, n_stg;       // n_stg = staging tiles in total (epi_groups x 1 or 2)
+    int nacc;                    // TMEM accumulators: 2 of n_cta <= 256 columns, or 1 of up to 512
+    int epi_colsplit;            // 1: both epilogue groups drain every item, alternating 64-column blocks
     int smem_bytes;
 };
 
-inline BlockPlanOut plan_block(const BlockPlanIn& q) {
-    BlockPlanOut p{};
-    const int NI = q.tile ? 2 : 1, TH = 8, TW = q.tile ? 8 : 16;
-    const int IH = (TH - 1) * q.stride + q.ksize, IW = (TW - 1) * q.stride + q.ksize;
-    p.kblocks = (q.c_in + kPlanKblk - 1) / kPlanKblk;
-    p.cin_pad = p.kblocks * kPlanKblk;
-    // Split the output channels into items (each item recomputes the depthwise half for its 128 pixels, so splitting is
-    // not free).  Candidates: n_cta <= 256 (two TMEM accumulators), multiples of 64 when there is more than one split
-    // (the epilogue moves whole [128 px][64 ch] tiles and must not touch a neighbouring split's columns).  Pick the
-    // candidate with the smallest modelled kernel time: rounds over the 148 SMs x (K-blocks x max(depthwise, MMA) cycles)
-    // + the last item's exposed epilogue.  The per-K-block cycle counts are the measured ones (profiles/r01_trace_*).
-    const int cout_pad = (q.c_out + 15) / 16 * 16;
-    int splits = 1;
-    {
-        const long dw_c = q.ksize == 5 ? 2100 : (q.stride == 2 ? 1200 : 1000);
-        long best_t = -1;
-        for (int n_cta = 256; n_cta >= 64; n_cta -= 64) {
-            int sp = (cout_pad + n_cta - 1) / n_cta, nc = n_cta;
-            if (sp == 1) nc = cout_pad;                              // a single split needs no 64-alignment
-            if (sp == 1 && cout_pad > 256) continue;
-            if (q.head && sp > 1) continue;
-            const long items = (long)q.n_tiles * sp;
-            const long rounds = (items + 147) / 148;
-            const long mma_c = 2L * nc;                              // 128 x nc x 64 MACs at 4096 MAC/clk
-            const long kb_c = (dw_c > mma_c ? dw_c : mma_c) + 100;
-            const long t = rounds * p.kblocks * kb_c + 45L * nc;
-            if (best_t < 0 || t < best_t) { best_t = t; splits = sp; p.n_cta = nc; }
-        }
-        if (cout_pad <= 64 || q.head) { splits = 1; p.n_cta = cout_pad; }
-    }
-    p.splits = splits;
-    p.items = q.n_tiles * splits;
-    p.cpad_all = p.n_cta * splits;
-    p.tmem_cols = 32;
-    while (p.tmem_cols < 2 * p.n_cta) p.tmem_cols *= 2;
-    p.in_stage_bytes = NI * IH * IW * 128;
-    p.dwp_bytes = q.ksize * q.ksize * 128 + 512;
-    p.in_stage_stride = (p.in_stage_bytes + p.dwp_bytes + 127) / 128 * 128;
-
-    // small search over ring depths / weight sub-block width / epilogue organisation, scored by what matters for
-    // the block at hand (stride-2 blocks stage 72 KB of input per K-block and leave little room; single-K-block
-    // blocks want a deep A ring to hide the serial latency of the MMA issue thread)
+// Shared-memory search for one choice of (splits, n_cta): ring depths / weight sub-block width / epilogue organisation,
+// scored by what matters for the block at hand (stride-2 blocks stage 72 KB of input per K-block and leave little room;
+// single-K-block blocks want a deep A ring to hide the serial latency of the MMA issue thread).
+inline bool plan_block_smem(const BlockPlanIn& q, BlockPlanOut& p, bool allow_narrow) {
+    const int splits = p.splits;
     const int fixed = q.barrier_bytes + 2048 + (q.head ? 3 : 2) * p.cpad_all * 4;      // 2048: two 1 KB alignment slacks
     const int total = kPlanSmemBudget - fixed;
     long best = -(1L << 60);
@@ -78,6 +45,7 @@ inline BlockPlanOut plan_block(const BlockPlanIn& q) {
             const int groups = q.head ? 2 : (eg >= 2 ? 2 : 1);
             const int n_stg = q.head ? 0 : groups * ((eg & 1) ? 2 : 1);
             if (q.head && eg != 1) continue;
+            if (p.nacc == 1 && groups != 2) continue;      // a single 512-column accumulator is drained by both groups together
             const int avail = total - s_a * kPlanAStage - n_stg * kPlanStg;
             for (int bn = bn_top;; bn = (bn / 2 + 15) / 16 * 16) {
                 const int nb = (p.n_cta + bn - 1) / bn;
@@ -98,7 +66,13 @@ inline BlockPlanOut plan_block(const BlockPlanIn& q) {
                         long score = (long)bn_eff * 100 + (bn >= 256 ? 500 : 0) + (s_in > 4 ? 4 : s_in) * 2500 +
                                      s_a * (p.kblocks <= 2 ? 1500 : 400) + groups * 2500 + n_stg * 300 + (res ? 1000 : 0) +
                                      b_ahead2 * 1800;
-                        if (bn < 64 && bn < bn_top) score -= 20000;          // narrow MMAs are a last resort
+                        if (p.n_cta > 256)       // 64 KB of weights per K-block: the weight ring needs the room more than the input ring
+                            score = (long)bn_eff * 100 + (bn >= 256 ? 500 : 0) + (s_in > 3 ? 3 : s_in) * 2500 + s_a * 400 + n_stg * 300 +
+                                    b_ahead2 * 3000;
+                        if (bn < 64 && bn < bn_top) {                        // narrow MMAs are a last resort
+                            if (!allow_narrow) continue;
+                            score -= 20000;
+                        }
                         if (score > best) {
                             found = true; best = score;
                             p.s_a = s_a; p.n_stg = n_stg; p.epi_groups = groups; p.s_in = s_in; p.s_b = s_b; p.bn = bn; p.b_resident = res;
@@ -107,11 +81,81 @@ inline BlockPlanOut plan_block(const BlockPlanIn& q) {
                 if (bn <= 16) break;
             }
         }
-    p.ok = found ? 1 : 0;
-    if (!found) return p;
+    if (!found) return false;
     p.nb = (p.n_cta + p.bn - 1) / p.bn;
     p.b_stage_bytes = p.bn * 128;
     p.smem_bytes = p.s_a * kPlanAStage + p.s_b * p.b_stage_bytes + p.s_in * p.in_stage_stride + p.n_stg * kPlanStg + fixed;
+    // both epilogue groups drain every item together, alternating 64-column blocks, whenever there are at least two
+    // blocks: same throughput as taking alternate items, half the exposed drain after a CTA's last item
+    p.epi_colsplit = (!q.head && p.epi_groups == 2 && p.n_cta > 64 && (!q.no_colsplit || p.nacc == 1)) ? 1 : 0;
+    return true;
+}
+
+inline BlockPlanOut plan_block(const BlockPlanIn& q) {
+    BlockPlanOut p{};
+    const int NI = q.tile ? 2 : 1, TH = 8, TW = q.tile ? 8 : 16;
+    const int IH = (TH - 1) * q.stride + q.ksize, IW = (TW - 1) * q.stride + q.ksize;
+    p.kblocks = (q.c_in + kPlanKblk - 1) / kPlanKblk;
+    p.cin_pad = p.kblocks * kPlanKblk;
+    p.in_stage_bytes = NI * IH * IW * 128;
+    p.dwp_bytes = q.ksize * q.ksize * 128 + 512;
+    p.in_stage_stride = (p.in_stage_bytes + p.dwp_bytes + 127) / 128 * 128;
+    // Split the output channels into items (each item recomputes the depthwise half for its 128 pixels and reloads the
+    // input tile, so splitting is not free).  Candidates: n_cta <= 512 (the whole TMEM as one accumulator; <= 256 leaves
+    // room for two and overlaps the next item's MMAs with this item's drain), multiples of 64 when there is more than
+    // one split (the epilogue moves whole [128 px][64 ch] tiles and must not touch a neighbouring split's columns).
+    // Candidates are tried in the order of their modelled kernel time
+    //     rounds over the 148 SMs x K-blocks x max(depthwise, MMA, L2 -> SM operand traffic) + exposed drain of the last item
+    // until one fits shared memory.  Per-K-block cycles are measured ones (profiles/r01_trace_*); the operand-traffic term
+    // is chip-wide: the L2 delivers ~6300 B/clk to all SMs together (B300_MICROARCH.md), ~5500 sustained here, and the
+    // 14x14 blocks sit on it (conv7: 148 CTAs x 57 KB per K-block every 1750 cycles).
+    const int cout_pad = (q.c_out + 15) / 16 * 16;
+    struct Cand { long t; int sp, nc; };
+    Cand cands[8];
+    int n_cands = 0;
+    if (cout_pad <= 64 || q.head) {
+        cands[n_cands++] = Cand{0, 1, cout_pad};
+    } else {
+        const long dw_c = q.ksize == 5 ? 2100 : (q.stride == 2 ? 1200 : 1000);
+        for (int n_cta = 512; n_cta >= 64; n_cta -= 64) {
+            int sp = (cout_pad + n_cta - 1) / n_cta, nc = n_cta;
+            if (sp == 1) nc = cout_pad;                              // a single split needs no 64-alignment
+            if (sp == 1 && cout_pad > 512) continue;
+            if (sp == 1 && n_cta - 64 >= cout_pad) continue;         // same plan as the next smaller candidate
+            if (q.max_n_cta > 0 && nc > q.max_n_cta && !(sp == 1 && cout_pad <= 256)) continue;
+            const long items = (long)q.n_tiles * sp;
+            const long rounds = (items + 147) / 148;
+            const long active = items < 148 ? items : 148;
+            const long mma_c = 2L * nc;                              // 128 x nc x 64 MACs at 4096 MAC/clk
+            const long l2_c = active * (p.in_stage_bytes + 128L * nc) / 5500;
+            long kb_c = dw_c > mma_c ? dw_c : mma_c;
+            if (l2_c > kb_c) kb_c = l2_c;
+            const long drain = (nc > 64 ? 23L : 45L) * nc;           // two epilogue groups share an item's column blocks
+            const long t = rounds * p.kblocks * (kb_c + 100) + drain;
+            int at = n_cands++;
+            while (at > 0 && cands[at - 1].t > t) { cands[at] = cands[at - 1]; --at; }
+            cands[at] = Cand{t, sp, nc};
+        }
+    }
+    for (int i = 0; i < n_cands; ++i) {
+        p.splits = cands[i].sp; p.n_cta = cands[i].nc;
+        p.items = q.n_tiles * p.splits;
+        p.cpad_all = p.n_cta * p.splits;
+        p.nacc = p.n_cta > 256 ? 1 : 2;
+        p.tmem_cols = 32;
+        while (p.tmem_cols < p.nacc * p.n_cta) p.tmem_cols *= 2;
+        if (plan_block_smem(q, p, false)) { p.ok = 1; return p; }
+    }
+    for (int i = 0; i < n_cands; ++i) {                              // nothing fits with full-width MMAs: accept narrow ones
+        p.splits = cands[i].sp; p.n_cta = cands[i].nc;
+        p.items = q.n_tiles * p.splits;
+        p.cpad_all = p.n_cta * p.splits;
+        p.nacc = p.n_cta > 256 ? 1 : 2;
+        p.tmem_cols = 32;
+        while (p.tmem_cols < p.nacc * p.n_cta) p.tmem_cols *= 2;
+        if (plan_block_smem(q, p, true)) { p.ok = 1; return p; }
+    }
+    p.ok = 0;
     return p;
 }
 

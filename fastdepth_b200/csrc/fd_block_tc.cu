@@ -24,6 +24,7 @@
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -69,8 +70,11 @@ struct TcParams {
     int dwp_bytes;        // bytes of one K-block's depthwise parameter block
     int cpad_all;         // n_cta * splits: padded length of the pointwise BN vectors
     int n_stg;            // epilogue staging tiles (16 KB each) in total: epi_groups x (2 or 1)
+    int epi_colsplit;     // 1: both epilogue groups drain EVERY item, group g taking the 64-column blocks g, g+2, ... (halves the
+                          //    exposed drain after a CTA's last item; needed when one 512-column accumulator is all there is)
     int epi_groups;       // 2: two groups of four epilogue warps take alternate items; 1: one group takes all (smem is tight)
     int out_pitch, skip_pitch;   // elements between pixels of the output / skip tensors (>= c_out: channel slice of a concat buffer)
+    int sleep_ns;         // > 0: latency-tolerant waits sleep this long between probes instead of spinning
     int epi_tma;          // 1: staging tiles leave through TMA tensor stores (4 strided views for nearest-x2 upsampling)
     int epi_red;          // 1: ... as element-wise ADD into the skip tensor, which then IS the block's output (in place)
     unsigned long long mg_splits, mg_tx, mg_ty;   // 2^40 / d reciprocals for the item -> tile decode
@@ -145,7 +149,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         for (int i = 0; i < TC_MAX_IN; ++i) { mbar_init(smem_u32(&bars->in_full[i]), 1); mbar_init(smem_u32(&bars->in_empty[i]), TC_DW_WARPS); }
         for (int i = 0; i < TC_MAX_A; ++i) { mbar_init(smem_u32(&bars->a_full[i]), TC_DW_WARPS); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
         for (int i = 0; i < TC_MAX_B; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), TC_EPI_WARPS / 2); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), p.epi_colsplit ? TC_EPI_WARPS : TC_EPI_WARPS / 2); }
         fence_barrier_init();
     }
     if (warp == TC_WARP_MMA) tmem_alloc(smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);     // MMA warp owns TMEM
@@ -176,7 +180,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                 const ItemCoord c = decode_item(p, w, NI, TH, TW);
                 for (int kb = 0; kb < p.kblocks; ++kb, rin.next((uint32_t)p.s_in)) {
                     const uint32_t s = rin.s, ph = rin.ph;
-                    mbar_wait(smem_u32(&bars->in_empty[s]), ph ^ 1u);
+                    mbar_wait_sleep(smem_u32(&bars->in_empty[s]), ph ^ 1u, (uint32_t)p.sleep_ns >> 2);
                     mbar_expect_tx(smem_u32(&bars->in_full[s]), (uint32_t)(p.in_stage_bytes + p.dwp_bytes));
                     tma_load_4d(smem_base + in_off + s * p.in_stage_stride, &tm_in, smem_u32(&bars->in_full[s]), kb * TC_KBLK,
                                 c.ox0 * STRIDE - PAD, c.oy0 * STRIDE - PAD, c.img0);
@@ -199,7 +203,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                             sb = (uint32_t)(kb * p.nb + nbi);
                         } else {
                             sb = rb.s;
-                            mbar_wait(smem_u32(&bars->b_empty[sb]), rb.ph ^ 1u);
+                            mbar_wait_sleep(smem_u32(&bars->b_empty[sb]), rb.ph ^ 1u, (uint32_t)p.sleep_ns >> 2);
                             rb.next((uint32_t)p.s_b);
                         }
                         mbar_expect_tx(smem_u32(&bars->b_full[sb]), (uint32_t)p.b_stage_bytes);
@@ -341,14 +345,16 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         const int ngrp = p.epi_groups;                     // 2, or 1 when shared memory is tight (group 1 then idles)
         const int n_stg_g = p.head ? 0 : p.n_stg / ngrp;   // staging tiles of this group: 1 or 2
         const uint32_t stg_grp = stg_off + (uint32_t)grp * (uint32_t)n_stg_g * 16384u;
-        uint32_t ab = ngrp == 2 ? (uint32_t)grp : 0u, pa = 0;   // accumulator buffer and its mbarrier phase
+        const bool cs = p.epi_colsplit != 0;               // both groups on every item, alternating column blocks
+        uint32_t ab = (ngrp == 2 && !cs) ? (uint32_t)grp : 0u, pa = 0;   // accumulator buffer and its mbarrier phase
         int tr = 0;
         uint32_t stg_flip = 0;
-        for (int w = blockIdx.x + grp * gridDim.x; grp < ngrp && w < p.items; w += ngrp * gridDim.x) {
+        const int w_step = (cs ? 1 : ngrp) * (int)gridDim.x;
+        for (int w = blockIdx.x + (cs ? 0 : grp) * gridDim.x; grp < ngrp && w < p.items; w += w_step) {
             const ItemCoord c = decode_item(p, w, NI, TH, TW);
             const int img = c.img0 + e_ni, oy = c.oy0 + e_ty, ox = c.ox0 + e_tx;
             const bool valid = img < p.n && oy < p.h_out && ox < p.w_out;
-            mbar_wait(smem_u32(&bars->acc_full[ab]), pa);
+            mbar_wait_sleep(smem_u32(&bars->acc_full[ab]), pa, (uint32_t)p.sleep_ns);
             tc_fence_after();
             if (grp == 0 && elected) TC_TRACE(6, tr);
             const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + ab * (uint32_t)p.n_cta;
@@ -360,7 +366,9 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                 //  B: the tile leaves through TMA tensor stores (or, as a fallback, coalesced 16-byte LSU stores)
                 const int nblk = (p.n_cta + 63) >> 6;
                 const float2* aff = s_pw_affine + c.n0;                  // this item's (scale, bias) pairs
-                for (int cb = 0; cb < nblk; ++cb) {
+                const int cb_step = cs ? 2 : 1;
+                const int cb_last = cs ? ((nblk - 1 - grp) & ~1) + grp : nblk - 1;     // this group's last block of the item
+                for (int cb = cs ? grp : 0; cb < nblk; cb += cb_step) {
                     uint8_t* stg = smem + stg_grp + (n_stg_g == 2 ? (stg_flip & 1u) * 16384u : 0u);
                     ++stg_flip;
                     if (n_stg_g == 1 && stg_flip > 1) {                  // single staging buffer: wait until it is free again
@@ -392,7 +400,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                             }
                         }
                     }
-                    if (cb == nblk - 1) {                                 // last TMEM read of this item: release the accumulator early
+                    if (cb == cb_last) {                                  // last TMEM read of this item: release the accumulator early
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));
@@ -509,7 +517,9 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                 }
             }
             if (grp == 0 && elected) { TC_TRACE(7, tr); ++tr; }
-            if (ngrp == 2) { pa ^= 1u; } else { ab ^= 1u; if (ab == 0u) pa ^= 1u; }
+            if (cs) {                                      // every item: next accumulator (or the same one, next phase)
+                if (p.nacc == 2) { ab ^= 1u; if (ab == 0u) pa ^= 1u; } else { pa ^= 1u; }
+            } else if (ngrp == 2) { pa ^= 1u; } else { ab ^= 1u; if (ab == 0u) pa ^= 1u; }
         }
         if (p.epi_tma && elected) bulk_wait_all();                       // all tensor stores of this group have landed
     }
@@ -526,6 +536,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
 // host side
 // ----------------------------------------------------------------------------------------------
 int g_use_pdl = 1;
+int g_wait_sleep_ns = 100;
 
 PFN_encodeTiled get_tensor_map_encoder() {
     static PFN_encodeTiled fn = nullptr;
@@ -549,6 +560,14 @@ struct BlockTcPlan {
     float* head_w = nullptr;
     std::string name;
 };
+
+// experiment knobs (environment, read when a plan is built): FD_TC_MAX_NCTA=<n>, FD_TC_NO_COLSPLIT=1
+static void plan_env_knobs(BlockPlanIn& q) {
+    const char* a = getenv("FD_TC_MAX_NCTA");
+    const char* b = getenv("FD_TC_NO_COLSPLIT");
+    q.max_n_cta = a ? atoi(a) : 0;
+    q.no_colsplit = (b && *b == '1') ? 1 : 0;
+}
 
 static int pick_tile(const StageGeom& g) {
     // 2 images x 8x8 when a whole image fits an 8x8 box (7x7 stages), else 1 image x 8 rows x 16 cols
@@ -577,6 +596,7 @@ static int launch_inst2(BlockTcPlan* bp, cudaStream_t st) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
+    bp->p.sleep_ns = g_wait_sleep_ns;
     FD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, bp->tm_in, bp->tm_w, bp->tm_o[0], bp->tm_o[1], bp->tm_o[2], bp->tm_o[3], bp->p));
     FD_CUDA_OK(cudaGetLastError());
     return FD_OK;
@@ -619,6 +639,7 @@ BlockPlanOut block_tc_debug_plan(int ksize, int stride, int h_out, int w_out, in
     const int NI = q.tile ? 2 : 1, TW = q.tile ? 8 : 16;
     q.n_tiles = ((w_out + TW - 1) / TW) * ((h_out + 7) / 8) * ((n + NI - 1) / NI);
     q.barrier_bytes = (int)sizeof(TcBarriers);
+    plan_env_knobs(q);
     return plan_block(q);
 }
 
@@ -700,10 +721,12 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
     BlockPlanIn pin{};
     pin.ksize = g.ksize; pin.stride = g.stride; pin.tile = bp->tile; pin.c_in = g.c_in; pin.c_out = g.c_out; pin.n_tiles = n_tiles;
     pin.head = p.head; pin.barrier_bytes = (int)sizeof(TcBarriers);
+    plan_env_knobs(pin);
     const BlockPlanOut po = plan_block(pin);
     if (!po.ok) { delete bp; return fail(FD_ERR_UNSUPPORTED, "fused block does not fit shared memory"); }
     const int splits = po.splits;
-    p.n_cta = po.n_cta; p.splits = po.splits; p.items = po.items; p.nacc = 2; p.tmem_cols = po.tmem_cols;
+    p.n_cta = po.n_cta; p.splits = po.splits; p.items = po.items; p.nacc = po.nacc; p.tmem_cols = po.tmem_cols;
+    p.epi_colsplit = po.epi_colsplit;
     p.in_stage_bytes = po.in_stage_bytes; p.dwp_bytes = po.dwp_bytes; p.in_stage_stride = po.in_stage_stride; p.cpad_all = po.cpad_all;
     p.s_a = po.s_a; p.n_stg = po.n_stg; p.epi_groups = po.epi_groups; p.s_in = po.s_in; p.s_b = po.s_b; p.bn = po.bn; p.nb = po.nb;
     p.b_resident = po.b_resident; p.b_stage_bytes = po.b_stage_bytes;
@@ -777,9 +800,9 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
         }
     }
     char buf[160];
-    snprintf(buf, sizeof(buf), "block_tc<k%d,s%d,%s>%s%s%s[n%dx%d,bn%d%s,kb%d,in%d,a%d,e%dx%d]", g.ksize, g.stride, bp->tile ? "2x8x8" : "1x8x16",
+    snprintf(buf, sizeof(buf), "block_tc<k%d,s%d,%s>%s%s%s[n%dx%d,bn%d%s,kb%d,in%d,a%d,b%d,e%dx%d%s]", g.ksize, g.stride, bp->tile ? "2x8x8" : "1x8x16",
              g.upsample ? "+up2x" : "", a.skip ? (p.epi_red ? "+skip(red)" : "+skip") : "", p.head ? "+head" : (p.epi_tma ? "+tmast" : ""), p.n_cta, p.splits, p.bn,
-             p.b_resident ? "r" : "", p.kblocks, p.s_in, p.s_a, p.epi_groups, p.head ? 0 : p.n_stg / p.epi_groups);
+             p.b_resident ? "r" : "", p.kblocks, p.s_in, p.s_a, p.s_b, p.epi_groups, p.head ? 0 : p.n_stg / p.epi_groups, p.epi_colsplit ? "c" : "");
     bp->name = buf;
     *out = bp;
     return FD_OK;

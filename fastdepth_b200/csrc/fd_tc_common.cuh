@@ -33,6 +33,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity), "r"(1000000u) : "memory");
 }
+// Wait for roles that can afford wake-up latency (epilogue warps waiting for an accumulator, the TMA producer waiting for
+// a free stage).  ncu's source view of conv7 showed mbar_wait's try_wait/NANOSLEEP.SYNCS pair re-issuing every ~27 cycles
+// per waiting warp whatever the suspend hint says -- a quarter of all warp instructions of the kernel, taken from the
+// schedulers the depthwise warps issue on.  A plain timed sleep between probes really parks the warp.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
+    if (ns == 0u) { mbar_wait(bar, parity); return; }
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(ns);
+    }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

@@ -105,7 +105,10 @@ int fd_plan_set_stage_weights(fd_plan* plan, int stage,
  *                (TMA reduce-add); the skip source's stage buffer then holds the decoder output
  *                after fd_forward (set 0 for stage-by-stage inspection)  [default 1]
  *   "pdl"        1 = tensor-core kernels are launched with programmatic dependent launch so that each
- *                kernel's prologue overlaps the previous kernel's tail  [default 1]            */
+ *                kernel's prologue overlaps the previous kernel's tail  [default 1]
+ *   "wait_sleep_ns" > 0: latency-tolerant roles of the fused block kernel (epilogue warps waiting for an
+ *                accumulator, TMA producer waiting for a free stage) sleep this many ns between barrier
+ *                probes instead of spinning on the schedulers the depthwise warps use  [default 100]   */
 int fd_plan_set_option(fd_plan* plan, const char* name, int value);
 int fd_plan_get_option(fd_plan* plan, const char* name, int* value);
 
