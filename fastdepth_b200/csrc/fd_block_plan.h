@@ -16,6 +16,7 @@ struct BlockPlanIn {
     int head;                    // decode_conv6 folded into the epilogue
     int barrier_bytes;           // sizeof(TcBarriers)
     int max_n_cta;               // 0 = no limit; experiments: cap the output channels per item (FD_TC_MAX_NCTA)
+    int no_wide;                 // experiments: 1 = a single epilogue group stays four warps (FD_TC_NO_WIDE)
     int no_colsplit;             // experiments: 1 = epilogue groups take alternate items even when they could share (FD_TC_NO_COLSPLIT)
 };
 struct BlockPlanOut {
@@ -26,6 +27,7 @@ struct BlockPlanOut {
     int epi_groups, n_stg;       // n_stg = staging tiles in total (epi_groups x 1 or 2)
     int nacc;                    // TMEM accumulators: 2 of n_cta <= 256 columns, or 1 of up to 512
     int epi_colsplit;            // 1: both epilogue groups drain every item, alternating 64-column blocks
+    int epi_wide;                // 1: one staging tile, all eight epilogue warps on it (32 columns per warp)
     int smem_bytes;
 };
 
@@ -88,6 +90,9 @@ inline bool plan_block_smem(const BlockPlanIn& q, BlockPlanOut& p, bool allow_na
     // both epilogue groups drain every item together, alternating 64-column blocks, whenever there are at least two
     // blocks: same throughput as taking alternate items, half the exposed drain after a CTA's last item
     p.epi_colsplit = (!q.head && p.epi_groups == 2 && p.n_cta > 64 && (!q.no_colsplit || p.nacc == 1)) ? 1 : 0;
+    // only one staging tile fits (stride-2 blocks): all eight warps share it, each TMEM lane quarter's two warps split the
+    // block's 64 columns -- these blocks were bound by a single four-warp group draining 3 400 cycles per block
+    p.epi_wide = (!q.head && p.epi_groups == 1 && !q.no_wide) ? 1 : 0;
     return true;
 }
 

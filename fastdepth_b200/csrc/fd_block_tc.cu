@@ -72,6 +72,8 @@ struct TcParams {
     int n_stg;            // epilogue staging tiles (16 KB each) in total: epi_groups x (2 or 1)
     int epi_colsplit;     // 1: both epilogue groups drain EVERY item, group g taking the 64-column blocks g, g+2, ... (halves the
                           //    exposed drain after a CTA's last item; needed when one 512-column accumulator is all there is)
+    int epi_wide;         // 1 (with epi_groups == 1): all eight epilogue warps work on ONE staging tile, the two warps of a TMEM
+                          //    lane quarter taking 32 of each block's 64 columns -- twice the drain rate where only one tile fits
     int epi_groups;       // 2: two groups of four epilogue warps take alternate items; 1: one group takes all (smem is tight)
     int out_pitch, skip_pitch;   // elements between pixels of the output / skip tensors (>= c_out: channel slice of a concat buffer)
     int sleep_ns;         // > 0: latency-tolerant waits sleep this long between probes instead of spinning
@@ -149,7 +151,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         for (int i = 0; i < TC_MAX_IN; ++i) { mbar_init(smem_u32(&bars->in_full[i]), 1); mbar_init(smem_u32(&bars->in_empty[i]), TC_DW_WARPS); }
         for (int i = 0; i < TC_MAX_A; ++i) { mbar_init(smem_u32(&bars->a_full[i]), TC_DW_WARPS); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
         for (int i = 0; i < TC_MAX_B; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), p.epi_colsplit ? TC_EPI_WARPS : TC_EPI_WARPS / 2); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), (p.epi_colsplit || p.epi_wide) ? TC_EPI_WARPS : TC_EPI_WARPS / 2); }
         fence_barrier_init();
     }
     if (warp == TC_WARP_MMA) tmem_alloc(smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);     // MMA warp owns TMEM
@@ -338,19 +340,21 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         const int q = ew & 3, grp = ew >> 2;               // TMEM lane quarter (== warp % 4), group / accumulator index
         const int m = q * 32 + lane;                       // accumulator row == pixel of the tile
         const int e_ni = m / (TH * TW), e_ty = (m / TW) % TH, e_tx = m % TW;
-        const uint32_t bar_id = 1u + (uint32_t)grp;        // named barrier of this group (128 threads)
-        const bool elected = q == 0 && lane == 0;          // issues this group's tensor stores
+        const bool wide = p.epi_wide != 0;                 // one group of eight warps, warp pair (w, w+4) splits each block's columns
+        const uint32_t bar_id = wide ? 1u : 1u + (uint32_t)grp;     // named barrier of this group
+        const uint32_t bar_n = wide ? 256u : 128u;                  // ... and its thread count
+        const bool elected = q == 0 && lane == 0 && (!wide || grp == 0);   // issues this group's tensor stores
         T* __restrict__ outp = reinterpret_cast<T*>(p.out);
         const T* __restrict__ skipp = reinterpret_cast<const T*>(p.skip);
         const int ngrp = p.epi_groups;                     // 2, or 1 when shared memory is tight (group 1 then idles)
         const int n_stg_g = p.head ? 0 : p.n_stg / ngrp;   // staging tiles of this group: 1 or 2
-        const uint32_t stg_grp = stg_off + (uint32_t)grp * (uint32_t)n_stg_g * 16384u;
+        const uint32_t stg_grp = stg_off + (wide ? 0u : (uint32_t)grp) * (uint32_t)n_stg_g * 16384u;
         const bool cs = p.epi_colsplit != 0;               // both groups on every item, alternating column blocks
         uint32_t ab = (ngrp == 2 && !cs) ? (uint32_t)grp : 0u, pa = 0;   // accumulator buffer and its mbarrier phase
         int tr = 0;
         uint32_t stg_flip = 0;
         const int w_step = (cs ? 1 : ngrp) * (int)gridDim.x;
-        for (int w = blockIdx.x + (cs ? 0 : grp) * gridDim.x; grp < ngrp && w < p.items; w += w_step) {
+        for (int w = blockIdx.x + ((cs || wide) ? 0 : grp) * gridDim.x; (grp < ngrp || wide) && w < p.items; w += w_step) {
             const ItemCoord c = decode_item(p, w, NI, TH, TW);
             const int img = c.img0 + e_ni, oy = c.oy0 + e_ty, ox = c.ox0 + e_tx;
             const bool valid = img < p.n && oy < p.h_out && ox < p.w_out;
@@ -373,13 +377,13 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                     ++stg_flip;
                     if (n_stg_g == 1 && stg_flip > 1) {                  // single staging buffer: wait until it is free again
                         if (p.epi_tma && elected) bulk_wait_read0();
-                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory");
                     }
                     uint8_t* row = stg + m * 128;
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         const int col0 = cb * 64 + half * 32;             // first accumulator column of this half block
-                        if (col0 < p.n_cta) {
+                        if (col0 < p.n_cta && (!wide || half == grp)) {
                             uint32_t r[32];
                             const bool full = col0 + 32 <= p.n_cta;       // n_cta is a multiple of 16
                             if (full) tmem_ld32_sync(t_lane + col0, r);
@@ -412,7 +416,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                         fence_proxy_async();
                         if (grp == 0 && elected && cb == 0) TC_TRACE(9, tr);
                         if (elected) bulk_wait_read0();
-                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");    // staging tile complete + other buffer free
+                        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory");    // staging tile complete + other buffer free
                         if (grp == 0 && elected && cb == 0) TC_TRACE(10, tr);
                         if (elected) {
                             const uint32_t src = smem_u32(stg);
@@ -435,14 +439,15 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                         }
                         continue;
                     }
-                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");        // staging tile complete
-                    const int et = q * 32 + lane;                         // 0..127 over the group's four warps
+                    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory");        // staging tile complete
+                    const int et = (wide ? grp * 128 : 0) + q * 32 + lane;   // 0..127 (0..255) over the group's warps
                     const int ch = et & 7;                                // 16-byte chunk within the 64-channel block
                     const int ccol = cb * 64 + ch * 8;                    // accumulator column of that chunk
                     const bool cok = ccol < p.n_cta && c.n0 + ccol + 8 <= p.c_out;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const int rr = (et >> 3) + 16 * k;                // pixel row of the tile
+                        const int rr = (et >> 3) + (wide ? 32 : 16) * k;  // pixel row of the tile
+                        if (rr >= 128) break;
                         const int r_ni = rr / (TH * TW), r_ty = (rr / TW) % TH, r_tx = rr % TW;
                         const int pimg = c.img0 + r_ni, poy = c.oy0 + r_ty, pox = c.ox0 + r_tx;
                         if (!(cok && pimg < p.n && poy < p.h_out && pox < p.w_out)) continue;
@@ -565,6 +570,8 @@ struct BlockTcPlan {
 static void plan_env_knobs(BlockPlanIn& q) {
     const char* a = getenv("FD_TC_MAX_NCTA");
     const char* b = getenv("FD_TC_NO_COLSPLIT");
+    const char* c = getenv("FD_TC_NO_WIDE");
+    q.no_wide = (c && *c == '1') ? 1 : 0;
     q.max_n_cta = a ? atoi(a) : 0;
     q.no_colsplit = (b && *b == '1') ? 1 : 0;
 }
@@ -726,7 +733,7 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
     if (!po.ok) { delete bp; return fail(FD_ERR_UNSUPPORTED, "fused block does not fit shared memory"); }
     const int splits = po.splits;
     p.n_cta = po.n_cta; p.splits = po.splits; p.items = po.items; p.nacc = po.nacc; p.tmem_cols = po.tmem_cols;
-    p.epi_colsplit = po.epi_colsplit;
+    p.epi_colsplit = po.epi_colsplit; p.epi_wide = po.epi_wide;
     p.in_stage_bytes = po.in_stage_bytes; p.dwp_bytes = po.dwp_bytes; p.in_stage_stride = po.in_stage_stride; p.cpad_all = po.cpad_all;
     p.s_a = po.s_a; p.n_stg = po.n_stg; p.epi_groups = po.epi_groups; p.s_in = po.s_in; p.s_b = po.s_b; p.bn = po.bn; p.nb = po.nb;
     p.b_resident = po.b_resident; p.b_stage_bytes = po.b_stage_bytes;
@@ -802,7 +809,7 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
     char buf[160];
     snprintf(buf, sizeof(buf), "block_tc<k%d,s%d,%s>%s%s%s[n%dx%d,bn%d%s,kb%d,in%d,a%d,b%d,e%dx%d%s]", g.ksize, g.stride, bp->tile ? "2x8x8" : "1x8x16",
              g.upsample ? "+up2x" : "", a.skip ? (p.epi_red ? "+skip(red)" : "+skip") : "", p.head ? "+head" : (p.epi_tma ? "+tmast" : ""), p.n_cta, p.splits, p.bn,
-             p.b_resident ? "r" : "", p.kblocks, p.s_in, p.s_a, p.s_b, p.epi_groups, p.head ? 0 : p.n_stg / p.epi_groups, p.epi_colsplit ? "c" : "");
+             p.b_resident ? "r" : "", p.kblocks, p.s_in, p.s_a, p.s_b, p.epi_groups, p.head ? 0 : p.n_stg / p.epi_groups, p.epi_colsplit ? "c" : (p.epi_wide ? "w" : ""));
     bp->name = buf;
     *out = bp;
     return FD_OK;

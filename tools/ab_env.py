@@ -14,7 +14,7 @@ y = torch.empty((64, 1, 224, 224), dtype=torch.half, device='cuda')
 sp = torch.cuda.current_stream().cuda_stream
 ref = None
 for cfg in sys.argv[1:]:
-    for k in ('FD_TC_MAX_NCTA', 'FD_TC_NO_COLSPLIT'):
+    for k in ('FD_TC_MAX_NCTA', 'FD_TC_NO_COLSPLIT', 'FD_TC_NO_WIDE'):
         os.environ.pop(k, None)
     for kv in filter(None, cfg.split(',')):
         k, v = kv.split('='); os.environ[k] = v
