@@ -81,8 +81,7 @@ struct TcParams {
     int epi_red;          // 1: ... as element-wise ADD into the skip tensor, which then IS the block's output (in place)
     unsigned long long mg_splits, mg_tx, mg_ty;   // 2^40 / d reciprocals for the item -> tile decode
     const void* dwp;      // [kblocks] x { [k*k][64] 16-bit taps, [64] fp32 scale, [64] fp32 bias }
-                          //   (scale and bias pre-divided by 6 for ReLU6 stages: y = 6 * sat(acc*s/6 + b/6))
-    const float2* pw_affine;  // [cpad_all] (scale, bias) pairs, same /6 convention
+    const float2* pw_affine;  // [cpad_all / 2] x (scale, scale, bias, bias) of a channel pair
     const float* head_w;  // [cpad_all]
     unsigned long long* trace;   // debug timeline (fd_plan_trace_stage) or nullptr: [12 rows][TC_TRACE_N] SM clocks of CTA 0
 };
@@ -142,7 +141,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
     const uint32_t pw_off = stg_off + (uint32_t)p.n_stg * 16384u;
     const uint32_t bar_off = pw_off + (p.head ? 3u : 2u) * (uint32_t)p.cpad_all * 4u;
     TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem + bar_off);
-    float2* s_pw_affine = reinterpret_cast<float2*>(smem + pw_off);           // (scale, bias) per output channel
+    float2* s_pw_affine = reinterpret_cast<float2*>(smem + pw_off);           // (scale, scale, bias, bias) per output-channel pair
     float* s_head_w = reinterpret_cast<float*>(s_pw_affine + p.cpad_all);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -282,42 +281,84 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                 const uint8_t* in_s = stage + in_warp_off;
                 // this K-block's depthwise taps + folded BN for the lane's channel pair (landed with the tile)
                 const uint8_t* prm = stage + p.in_stage_bytes;
-                uint32_t wv[KS * KS];
-#pragma unroll
-                for (int i = 0; i < KS * KS; ++i) wv[i] = *reinterpret_cast<const uint32_t*>(prm + i * 128 + lane * 4);
-                const float2 sc = *reinterpret_cast<const float2*>(prm + KS * KS * 128 + lane * 8);
-                const float2 bi = *reinterpret_cast<const float2*>(prm + KS * KS * 128 + 256 + lane * 8);
+                const f32x2 sc = *reinterpret_cast<const f32x2*>(prm + KS * KS * 128 + lane * 8);        // (scale, scale) of the pair
+                const f32x2 bi = *reinterpret_cast<const f32x2*>(prm + KS * KS * 128 + 256 + lane * 8);  // (bias, bias)
                 // the A stage is normally free long before (deep ring): take it now so that every output row can be
                 // published the moment its last input row has been consumed -- the stores then drain during the math and
                 // the proxy fence at the end (a MEMBAR.ALL.CTA, ~36 cycles per store still in flight) finds few pending
                 mbar_wait(smem_u32(&bars->a_empty[sa]), pha ^ 1u);
                 uint8_t* a_s = smem + a_off + sa * TC_A_STAGE_BYTES;
-                float acc[4][4][2];
+                if constexpr (KS == 3) {
+                    // Inner product on FFMA2: every 16-bit word (the lane's channel pair) is widened to an fp32 pair once
+                    // (two HADD2.F32), then ONE two-wide FMA per pixel-tap instead of two half-rate FHFMA: 144 FFMA2 + 90
+                    // HADD2 against 288 FHFMA per 4x4 block (tools/fma2_tput.cu: 2.0x on the bare loop; bit-identical).
+                    f32x2 acc[4][4];
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+                    for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.f;
+                        for (int b = 0; b < 4; ++b) acc[a][b] = 0ull;
+                    f32x2 wq[KS][KS];
 #pragma unroll
-                for (int iy = 0; iy < IBH; ++iy) {
-                    uint32_t row[IBW];
-#pragma unroll
-                    for (int ix = 0; ix < IBW; ++ix) row[ix] = *reinterpret_cast<const uint32_t*>(in_s + (iy * IW + ix) * 128);
-#pragma unroll
-                    for (int oy = 0; oy < 4; ++oy) {
-                        const int ky = iy - oy * STRIDE;
-                        if (ky < 0 || ky >= KS) continue;
-#pragma unroll
-                        for (int ox = 0; ox < 4; ++ox)
+                    for (int iy = 0; iy < IBH; ++iy) {
+                        if (iy < KS) {                                    // a kernel row is widened when its first input row arrives
 #pragma unroll
                             for (int kx = 0; kx < KS; ++kx)
-                                MF::fma2(acc[oy][ox][0], acc[oy][ox][1], row[ox * STRIDE + kx], wv[ky * KS + kx]);
-                        if (ky == KS - 1) {                               // output row oy is complete: BN, act, pack, publish
+                                wq[iy][kx] = MF::widen(*reinterpret_cast<const uint32_t*>(prm + (iy * KS + kx) * 128 + lane * 4));
+                        }
+                        f32x2 row[IBW];
 #pragma unroll
-                            for (int ox = 0; ox < 4; ++ox) {
-                                const int m = (ni * TH + br * 4 + oy) * TW + bc * 4 + ox;
-                                const float lo = affine_act<RELU6>(acc[oy][ox][0], sc.x, bi.x);
-                                const float hi = affine_act<RELU6>(acc[oy][ox][1], sc.y, bi.y);
-                                *reinterpret_cast<uint32_t*>(a_s + m * 128 + (((lane >> 2) ^ (m & 7)) << 4) + ((lane & 3) << 2)) = MF::pack(lo, hi);
+                        for (int ix = 0; ix < IBW; ++ix) row[ix] = MF::widen(*reinterpret_cast<const uint32_t*>(in_s + (iy * IW + ix) * 128));
+#pragma unroll
+                        for (int oy = 0; oy < 4; ++oy) {
+                            const int ky = iy - oy * STRIDE;
+                            if (ky < 0 || ky >= KS) continue;
+#pragma unroll
+                            for (int ox = 0; ox < 4; ++ox)
+#pragma unroll
+                                for (int kx = 0; kx < KS; ++kx) ffma2(acc[oy][ox], row[ox * STRIDE + kx], wq[ky][kx]);
+                            if (ky == KS - 1) {                           // output row oy is complete: BN, act, pack, publish
+#pragma unroll
+                                for (int ox = 0; ox < 4; ++ox) {
+                                    const int m = (ni * TH + br * 4 + oy) * TW + bc * 4 + ox;
+                                    *reinterpret_cast<uint32_t*>(a_s + m * 128 + (((lane >> 2) ^ (m & 7)) << 4) + ((lane & 3) << 2)) =
+                                        MF::template pack_act<RELU6>(ffma2_abc(acc[oy][ox], sc, bi));
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    // 5x5: 25 fp32 tap pairs + 32 accumulators + an input row do not fit 96 registers, and walking the block
+                    // in two 4x2 passes doubles the loads and conversions (measured slower than FHFMA: decode_conv5 109 vs
+                    // 88 us) -- so the 5x5 blocks keep the mixed-precision FHFMA (16-bit x 16-bit + fp32, exact products)
+                    uint32_t wv[KS * KS];
+#pragma unroll
+                    for (int i = 0; i < KS * KS; ++i) wv[i] = *reinterpret_cast<const uint32_t*>(prm + i * 128 + lane * 4);
+                    float acc[4][4][2];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.f;
+#pragma unroll
+                    for (int iy = 0; iy < IBH; ++iy) {
+                        uint32_t row[IBW];
+#pragma unroll
+                        for (int ix = 0; ix < IBW; ++ix) row[ix] = *reinterpret_cast<const uint32_t*>(in_s + (iy * IW + ix) * 128);
+#pragma unroll
+                        for (int oy = 0; oy < 4; ++oy) {
+                            const int ky = iy - oy * STRIDE;
+                            if (ky < 0 || ky >= KS) continue;
+#pragma unroll
+                            for (int ox = 0; ox < 4; ++ox)
+#pragma unroll
+                                for (int kx = 0; kx < KS; ++kx)
+                                    MF::fma2(acc[oy][ox][0], acc[oy][ox][1], row[ox * STRIDE + kx], wv[ky * KS + kx]);
+                            if (ky == KS - 1) {                           // output row oy is complete: BN, act, pack, publish
+#pragma unroll
+                                for (int ox = 0; ox < 4; ++ox) {
+                                    const int m = (ni * TH + br * 4 + oy) * TW + bc * 4 + ox;
+                                    *reinterpret_cast<uint32_t*>(a_s + m * 128 + (((lane >> 2) ^ (m & 7)) << 4) + ((lane & 3) << 2)) =
+                                        MF::template pack_act<RELU6>(ffma2_abc(f32x2_make(acc[oy][ox][0], acc[oy][ox][1]), sc, bi));
+                                }
                             }
                         }
                     }
@@ -369,7 +410,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                 //     exactly like a SWIZZLE_128B tensor-map box)
                 //  B: the tile leaves through TMA tensor stores (or, as a fallback, coalesced 16-byte LSU stores)
                 const int nblk = (p.n_cta + 63) >> 6;
-                const float2* aff = s_pw_affine + c.n0;                  // this item's (scale, bias) pairs
+                const float2* aff = s_pw_affine + c.n0;                  // this item's BN affine, 8 bytes per channel
                 const int cb_step = cs ? 2 : 1;
                 const int cb_last = cs ? ((nblk - 1 - grp) & ~1) + grp : nblk - 1;     // this group's last block of the item
                 for (int cb = cs ? grp : 0; cb < nblk; cb += cb_step) {
@@ -393,13 +434,14 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                             for (int g = 0; g < 4; ++g) {                 // 8 channels -> one 16-byte chunk
                                 if (g >= 2 && !full) break;
                                 uint32_t pk[4];
-                                float4 af[4];                             // (s0, b0, s1, b1) x 4: independent broadcast loads first
+                                float4 af[4];                             // (s0, s1, b0, b1) x 4: independent broadcast loads first
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) af[j] = *reinterpret_cast<const float4*>(aff + col0 + g * 8 + 2 * j);
 #pragma unroll
                                 for (int j = 0; j < 4; ++j)
-                                    pk[j] = MF::pack(affine_act<RELU6>(__uint_as_float(r[g * 8 + 2 * j]), af[j].x, af[j].y),
-                                                     affine_act<RELU6>(__uint_as_float(r[g * 8 + 2 * j + 1]), af[j].z, af[j].w));
+                                    pk[j] = MF::template pack_act<RELU6>(ffma2_abc(
+                                        f32x2_make(__uint_as_float(r[g * 8 + 2 * j]), __uint_as_float(r[g * 8 + 2 * j + 1])),
+                                        f32x2_make(af[j].x, af[j].y), f32x2_make(af[j].z, af[j].w)));
                                 *reinterpret_cast<uint4*>(row + (((half * 4 + g) ^ (m & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                             }
                         }
@@ -503,8 +545,8 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                         const int c0 = b * 32 + 2 * j;
                         const float4 af = *reinterpret_cast<const float4*>(s_pw_affine + c0);
                         const float2 hw = *reinterpret_cast<const float2*>(s_head_w + c0);
-                        const float lo = affine_act<RELU6>(__uint_as_float(r[2 * j]), af.x, af.y);
-                        const float hi = affine_act<RELU6>(__uint_as_float(r[2 * j + 1]), af.z, af.w);
+                        const float lo = affine_act<RELU6>(__uint_as_float(r[2 * j]), af.x, af.z);
+                        const float hi = affine_act<RELU6>(__uint_as_float(r[2 * j + 1]), af.y, af.w);
                         const float2 rq = MF::unpack(MF::pack(lo, hi));      // decode_conv5's output is stored in 16 bits
                         dot = fmaf(rq.x, hw.x, dot);
                         dot = fmaf(rq.y, hw.y, dot);
@@ -688,7 +730,13 @@ __global__ void pack_dwp_kernel(const float* __restrict__ w, const float* __rest
 __global__ void pack_affine_kernel(const float* __restrict__ scale, const float* __restrict__ bias, float2* __restrict__ dst,
                                    int n_src, int n_dst, float post) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_dst) dst[i] = i < n_src ? make_float2(scale[i] * post, bias[i] * post) : make_float2(0.f, 0.f);
+    // per channel PAIR (2j, 2j+1): (scale, scale, bias, bias), so that one 16-byte load feeds an FFMA2
+    if (i < n_dst) {
+        const int pair = i >> 1, odd = i & 1;
+        float* d = reinterpret_cast<float*>(dst) + pair * 4;
+        d[odd] = i < n_src ? scale[i] * post : 0.f;
+        d[2 + odd] = i < n_src ? bias[i] * post : 0.f;
+    }
 }
 __global__ void pad_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_src, int n_dst) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -746,7 +794,7 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
 
     // packed / padded parameter copies (device -> device)
     int rc = FD_OK;
-    const float post = g.act == FD_ACT_RELU6 ? (1.0f / 6.0f) : 1.0f;    // ReLU6 is evaluated as 6 * sat(acc*s/6 + b/6)
+    const float post = 1.0f;
     auto magic = [](int d) { return (unsigned long long)((1ULL << 40) / (unsigned long long)d) + 1ULL; };
     p.mg_splits = magic(p.splits); p.mg_tx = magic(p.tiles_x); p.mg_ty = magic(p.tiles_y);
     if (cudaMalloc(&bp->dwp, (size_t)p.kblocks * p.dwp_bytes) != cudaSuccess) rc = fail(FD_ERR_CUDA, "cudaMalloc failed");

@@ -187,9 +187,10 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
                     uint32_t pk[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float4 af = *reinterpret_cast<const float4*>(s_affine + c0 + 2 * j);
-                        pk[j] = MF::pack(affine_act<true>(__uint_as_float(r[g * 8 + 2 * j]), af.x, af.y),
-                                         affine_act<true>(__uint_as_float(r[g * 8 + 2 * j + 1]), af.z, af.w));
+                        const float4 af = *reinterpret_cast<const float4*>(s_affine + c0 + 2 * j);     // (s0, s1, b0, b1)
+                        pk[j] = MF::template pack_act<true>(ffma2_abc(
+                            f32x2_make(__uint_as_float(r[g * 8 + 2 * j]), __uint_as_float(r[g * 8 + 2 * j + 1])),
+                            f32x2_make(af.x, af.y), f32x2_make(af.z, af.w)));
                     }
                     if (valid && c0 + 8 <= p.c_out) *reinterpret_cast<uint4*>(o + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
@@ -234,7 +235,12 @@ __global__ void pack_stem_w_kernel(const float* __restrict__ w27, T* __restrict_
 __global__ void pack_stem_affine_kernel(const float* __restrict__ scale, const float* __restrict__ bias, float2* __restrict__ dst,
                                         int c_out, int n_pad) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_pad) dst[i] = i < c_out ? make_float2(scale[i] * (1.f / 6.f), bias[i] * (1.f / 6.f)) : make_float2(0.f, 0.f);
+    // per channel PAIR (2j, 2j+1): (scale, scale, bias, bias), one 16-byte load feeds an FFMA2 (same layout as the block kernel)
+    if (i < n_pad) {
+        float* d = reinterpret_cast<float*>(dst) + (i >> 1) * 4;
+        d[i & 1] = i < c_out ? scale[i] : 0.f;
+        d[2 + (i & 1)] = i < c_out ? bias[i] : 0.f;
+    }
 }
 
 bool stem_tc_supported(int dtype, const StageGeom& g) {

@@ -171,9 +171,28 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
     return d;
 }
 
+// Packed fp32 pair (channel pair of one lane) and the Blackwell two-wide FMA, SASS FFMA2.  Measured on the depthwise inner
+// loop (tools/fma2_tput.cu, 8 warps per SM): converting each 16-bit operand pair to fp32 once and issuing ONE FFMA2 per
+// pixel-tap runs 2.0x faster than two FHFMA (fma.rn.f32.f16, which issues at half rate); the result is bit-identical
+// because a 16-bit x 16-bit product is exact in the fp32 FMA either way.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ void ffma2(f32x2& acc, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+__device__ __forceinline__ f32x2 ffma2_abc(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 f32x2_make(float lo, float hi) { return ((f32x2)__float_as_uint(hi) << 32) | (f32x2)__float_as_uint(lo); }
+__device__ __forceinline__ float f32x2_lo(f32x2 v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float f32x2_hi(f32x2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
+
 // mixed-precision FMA: exact 16-bit x 16-bit product added into fp32 (SASS FHFMA / FHFMA.BF16)
 template <typename T> struct MixFma;
 template <> struct MixFma<__half> {
+    __device__ __forceinline__ static f32x2 widen(uint32_t v) {           // two HADD2.F32
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
+        return f32x2_make(f.x, f.y);
+    }
     __device__ __forceinline__ static void fma2(float& lo, float& hi, uint32_t a, uint32_t b) {
         asm("{\n\t.reg .f16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %2;\n\tmov.b32 {bl, bh}, %3;\n\t"
             "fma.rn.f32.f16 %0, al, bl, %0;\n\tfma.rn.f32.f16 %1, ah, bh, %1;\n\t}" : "+f"(lo), "+f"(hi) : "r"(a), "r"(b));
@@ -183,9 +202,21 @@ template <> struct MixFma<__half> {
         return *reinterpret_cast<uint32_t*>(&h);
     }
     __device__ __forceinline__ static float2 unpack(uint32_t v) { return __half22float2(*reinterpret_cast<__half2*>(&v)); }
+    // round the fp32 pair to 16 bits with ReLU folded into the conversion (F2FP.RELU), ReLU6's upper clamp on the packed
+    // result (HMNMX2): clamping after rounding equals rounding after clamping because 0 and 6 are representable
+    template <bool RELU6>
+    __device__ __forceinline__ static uint32_t pack_act(f32x2 v) {
+        uint32_t h;
+        asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(f32x2_hi(v)), "f"(f32x2_lo(v)));
+        if (RELU6) asm("min.f16x2 %0, %0, %1;" : "+r"(h) : "r"(0x46004600u));
+        return h;
+    }
     static constexpr uint32_t kUmmaFormat = 0;   // F16
 };
 template <> struct MixFma<__nv_bfloat16> {
+    __device__ __forceinline__ static f32x2 widen(uint32_t v) {           // bf16 -> fp32 is a 16-bit shift
+        return f32x2_make(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+    }
     __device__ __forceinline__ static void fma2(float& lo, float& hi, uint32_t a, uint32_t b) {
         asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %2;\n\tmov.b32 {bl, bh}, %3;\n\t"
             "fma.rn.f32.bf16 %0, al, bl, %0;\n\tfma.rn.f32.bf16 %1, ah, bh, %1;\n\t}" : "+f"(lo), "+f"(hi) : "r"(a), "r"(b));
@@ -195,6 +226,13 @@ template <> struct MixFma<__nv_bfloat16> {
         return *reinterpret_cast<uint32_t*>(&h);
     }
     __device__ __forceinline__ static float2 unpack(uint32_t v) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v)); }
+    template <bool RELU6>
+    __device__ __forceinline__ static uint32_t pack_act(f32x2 v) {
+        uint32_t h;
+        asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(f32x2_hi(v)), "f"(f32x2_lo(v)));
+        if (RELU6) asm("min.bf16x2 %0, %0, %1;" : "+r"(h) : "r"(0x40C040C0u));
+        return h;
+    }
     static constexpr uint32_t kUmmaFormat = 1;   // BF16
 };
 
@@ -211,11 +249,11 @@ struct Ring {
 // exact w / d for w, d < 2^20 with mg = floor(2^40 / d) + 1
 __device__ __forceinline__ uint32_t fdiv40(uint32_t w, unsigned long long mg) { return (uint32_t)(((unsigned long long)w * mg) >> 40); }
 
-// BN affine + activation in two instructions: ReLU6 as 6*sat(acc*s/6 + b/6) (FFMA.SAT, FMUL), ReLU as max(fma, 0)
+// scalar BN affine + activation (head path only; the block paths do channel PAIRS: FFMA2 + MixFma::pack_act)
 template <bool RELU6>
 __device__ __forceinline__ float affine_act(float acc, float s, float b) {
-    if (RELU6) return 6.0f * __saturatef(fmaf(acc, s, b));
-    return fmaxf(fmaf(acc, s, b), 0.0f);
+    const float v = fmaxf(fmaf(acc, s, b), 0.0f);
+    return RELU6 ? fminf(v, 6.0f) : v;
 }
 
 
