@@ -7,7 +7,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libfastdepth_b200.so')
+LIB_PATH = os.environ.get('FD_B200_LIB') or os.path.join(HERE, 'libfastdepth_b200.so')   # env: developer A/B of kernel variants
 
 FD_F32, FD_F16, FD_BF16 = 0, 1, 2
 FD_STAGE_STEM, FD_STAGE_DWPW, FD_STAGE_HEAD = 0, 1, 2

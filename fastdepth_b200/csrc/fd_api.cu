@@ -93,7 +93,7 @@ struct fd_plan {
     std::vector<Stage> stages;
     std::vector<Step> steps;
     bool steps_valid = false;
-    int opt_path = 1, opt_fold_head = 1, opt_graph = 1, opt_tma_epilogue = 1, opt_inplace_skip = 1, opt_pdl = 1, opt_wait_sleep_ns = 100;
+    int opt_path = 1, opt_fold_head = 1, opt_graph = 1, opt_tma_epilogue = 1, opt_inplace_skip = 1, opt_pdl = 1, opt_wait_sleep_ns = 0;
     size_t workspace_bytes = 0;
     // fd_pipeline_*: host batches flow H2D -> forward -> D2H through kPipeSlots device slots on three streams
     struct PipeSlot { void* x = nullptr; void* y = nullptr; cudaEvent_t up = nullptr, done = nullptr, down = nullptr; bool busy = false; };

@@ -288,10 +288,17 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                 // the proxy fence at the end (a MEMBAR.ALL.CTA, ~36 cycles per store still in flight) finds few pending
                 mbar_wait(smem_u32(&bars->a_empty[sa]), pha ^ 1u);
                 uint8_t* a_s = smem + a_off + sa * TC_A_STAGE_BYTES;
-                if constexpr (KS == 3) {
+#ifdef FD_DW3_FHFMA                      // build-time A/B switch: 3x3 depthwise on FHFMA like the 5x5 (measured 1.2 % slower end to end)
+                constexpr bool kDwFfma2 = false;
+#else
+                constexpr bool kDwFfma2 = KS == 3;
+#endif
+                if constexpr (kDwFfma2) {
                     // Inner product on FFMA2: every 16-bit word (the lane's channel pair) is widened to an fp32 pair once
-                    // (two HADD2.F32), then ONE two-wide FMA per pixel-tap instead of two half-rate FHFMA: 144 FFMA2 + 90
-                    // HADD2 against 288 FHFMA per 4x4 block (tools/fma2_tput.cu: 2.0x on the bare loop; bit-identical).
+                    // (two HADD2.F32), then ONE two-wide FMA per pixel-tap instead of two FHFMA: 144 FFMA2 + 90 HADD2 against
+                    // 288 FHFMA per 4x4 block.  Bit-identical (a 16-bit x 16-bit product is exact in either FMA); FFMA2 issues
+                    // at well under 0.5 / clk so the FMA pipe time is about the same, the gain is the issue slots: measured
+                    // +1.2 % on the whole forward (conv1 68 -> 64 us).
                     f32x2 acc[4][4];
 #pragma unroll
                     for (int a = 0; a < 4; ++a)
@@ -327,9 +334,9 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                         }
                     }
                 } else {
-                    // 5x5: 25 fp32 tap pairs + 32 accumulators + an input row do not fit 96 registers, and walking the block
-                    // in two 4x2 passes doubles the loads and conversions (measured slower than FHFMA: decode_conv5 109 vs
-                    // 88 us) -- so the 5x5 blocks keep the mixed-precision FHFMA (16-bit x 16-bit + fp32, exact products)
+                    // 5x5 stays on the mixed-precision FHFMA (16-bit x 16-bit + fp32, exact products): tools/fma2_tput5.cu under
+                    // this kernel's register cap gives 2 118 cycles per 4x4 block for 800 FHFMA (~0.76 / clk / scheduler, close
+                    // to full rate) against 2 720 for 400 FFMA2 + 178 HADD2, and in the kernel decode_conv5 went 88 -> 109 us
                     uint32_t wv[KS * KS];
 #pragma unroll
                     for (int i = 0; i < KS * KS; ++i) wv[i] = *reinterpret_cast<const uint32_t*>(prm + i * 128 + lane * 4);
@@ -583,7 +590,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
 // host side
 // ----------------------------------------------------------------------------------------------
 int g_use_pdl = 1;
-int g_wait_sleep_ns = 100;
+int g_wait_sleep_ns = 0;
 
 PFN_encodeTiled get_tensor_map_encoder() {
     static PFN_encodeTiled fn = nullptr;

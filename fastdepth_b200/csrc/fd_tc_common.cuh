@@ -171,10 +171,10 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
     return d;
 }
 
-// Packed fp32 pair (channel pair of one lane) and the Blackwell two-wide FMA, SASS FFMA2.  Measured on the depthwise inner
-// loop (tools/fma2_tput.cu, 8 warps per SM): converting each 16-bit operand pair to fp32 once and issuing ONE FFMA2 per
-// pixel-tap runs 2.0x faster than two FHFMA (fma.rn.f32.f16, which issues at half rate); the result is bit-identical
-// because a 16-bit x 16-bit product is exact in the fp32 FMA either way.
+// Packed fp32 pair (channel pair of one lane) and the Blackwell two-wide FMA, SASS FFMA2: one instruction, two FMAs.  It
+// does not raise FMA throughput (32 lanes x 2 takes the pipe two cycles) but halves the instructions issued; used for the
+// BN affine of channel pairs everywhere and for the 3x3 depthwise inner product (tools/fma2_tput*.cu).
+// Results are bit-identical to FHFMA: a 16-bit x 16-bit product is exact in the fp32 FMA either way.
 typedef unsigned long long f32x2;
 __device__ __forceinline__ void ffma2(f32x2& acc, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
 __device__ __forceinline__ f32x2 ffma2_abc(f32x2 a, f32x2 b, f32x2 c) {

@@ -108,7 +108,8 @@ int fd_plan_set_stage_weights(fd_plan* plan, int stage,
  *                kernel's prologue overlaps the previous kernel's tail  [default 1]
  *   "wait_sleep_ns" > 0: latency-tolerant roles of the fused block kernel (epilogue warps waiting for an
  *                accumulator, TMA producer waiting for a free stage) sleep this many ns between barrier
- *                probes instead of spinning on the schedulers the depthwise warps use  [default 100]   */
+ *                probes instead of spinning (measured: no effect on B200, the spinning waiters do not
+ *                take issue slots the depthwise warps could use)  [default 0]   */
 int fd_plan_set_option(fd_plan* plan, const char* name, int value);
 int fd_plan_get_option(fd_plan* plan, const char* name, int* value);
 
