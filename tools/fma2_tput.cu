@@ -2,6 +2,9 @@
 //   mode 0: two FHFMA (fma.rn.f32.f16 with .H0/.H1 operands) per pixel-tap           (what block_tc_kernel does)
 //   mode 1: inputs / taps converted to fp32 pairs once, one FFMA2 (fma.rn.f32x2) per pixel-tap
 // 8 warps per SM (two per scheduler) like the kernel; 4 output pixels x 3 taps per input row of 6, 16 accumulator pairs.
+// CAVEAT: the asm statements are `volatile`, so the compiler keeps them in program order and both variants run latency-bound;
+// the 2.0x this prints (1383 vs 697 cycles) is the instruction-count ratio, not a pipe-throughput ratio.  fma2_tput5.cu has
+// the schedulable (non-volatile) version under the kernel's register cap; the in-kernel A/B (FD_DW3_FHFMA build) is +1.2 %.
 #include <cstdio>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
