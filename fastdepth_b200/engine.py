@@ -37,9 +37,17 @@ class SkipAddEngine:
 
     def set_option(self, name, value):
         """Forwarded to ``fd_plan_set_option`` on every current and future plan."""
+        prev = self.options.get(name)
         self.options[name] = int(value)
-        for p in self.plans.values():
-            p.set_option(name, value)
+        try:
+            for p in self.plans.values():
+                p.set_option(name, value)
+        except Exception:
+            if prev is None:
+                self.options.pop(name, None)
+            else:
+                self.options[name] = prev
+            raise
 
     # -- forward ---------------------------------------------------------------------------------
     def plan_for(self, x):

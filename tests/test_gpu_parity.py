@@ -287,3 +287,50 @@ def test_skipconcat(dtype, path):
     y8, _ = run(m2, x8, dtype, path)
     want = orc.skipconcat_forward(quantised_sd(sd, dtype), x8[[0, 7]].to(dtype).float())
     assert rel_err(y8[[0, 7]].float().cpu(), want) <= TOL[dtype]
+
+
+@pytest.mark.parametrize('widths', [synthetic.STOCK_WIDTHS, synthetic.PRUNED_WIDTHS], ids=['stock', 'pruned'])
+def test_epilogue_organisations_and_item_shapes_agree_bitwise(widths, monkeypatch):
+    """The planner's choices are scheduling only: alternate-item / column-split / eight-warp epilogues, one 512-column
+    accumulator vs two of 256, sleeping vs spinning waits must all produce the SAME bits (224x224 so that every block has
+    many items; the planner knobs are environment variables read when a plan is built)."""
+    from fastdepth_b200.engine import SkipAddEngine
+    m, _ = make_model(widths, torch.float16, (224, 224))
+    x = synthetic.synthetic_input(64, 224, 224, seed=11).cuda().half()     # the metric batch: only there does the planner
+    outs, kernels = [], []                                                  # pick one 512-column accumulator per 14x14 tile
+    for env, opts in (({}, {}),
+                      ({'FD_TC_MAX_NCTA': '256', 'FD_TC_NO_COLSPLIT': '1', 'FD_TC_NO_WIDE': '1'}, {}),
+                      ({'FD_TC_MAX_NCTA': '128'}, {'wait_sleep_ns': 200})):
+        for k in ('FD_TC_MAX_NCTA', 'FD_TC_NO_COLSPLIT', 'FD_TC_NO_WIDE'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng = SkipAddEngine(m)
+        for k, v in opts.items():
+            eng.set_option(k, v)
+        m.__dict__['_fd_engine'] = eng
+        with torch.no_grad():
+            outs.append(m(x).clone())
+        kernels.append(' '.join(s['kernel'] for s in next(iter(eng.plans.values())).steps()))
+    torch.cuda.synchronize()
+    assert 'c]' in kernels[0] and 'w]' in kernels[0], kernels[0]    # default plan uses column-split and eight-warp epilogues
+    assert 'c]' not in kernels[1] and 'w]' not in kernels[1] and 'n512' not in kernels[1], kernels[1]
+    assert kernels[0] != kernels[2], kernels[2]
+    if widths is synthetic.STOCK_WIDTHS:
+        assert 'n512x1' in kernels[0] and 'n512' not in kernels[2]
+    d1 = (outs[0].float() - outs[1].float()).abs().max().item()
+    d2 = (outs[0].float() - outs[2].float()).abs().max().item()
+    assert d1 == 0.0 and d2 == 0.0, (d1, d2, kernels[2])
+
+
+def test_option_validation():
+    from fastdepth_b200.engine import SkipAddEngine
+    m, _ = make_model(synthetic.STOCK_WIDTHS, torch.float16, (64, 96))
+    eng = SkipAddEngine(m)
+    eng.plan_for(synthetic.synthetic_input(1, 64, 96).cuda().half())
+    with pytest.raises(RuntimeError):
+        eng.set_option('wait_sleep_ns', -1)
+    with pytest.raises(RuntimeError):
+        eng.set_option('graph', 2)
+    with pytest.raises(RuntimeError):
+        eng.set_option('no_such_option', 1)
