@@ -12,13 +12,17 @@
 //                              [NI][IH][IW][64ch] (OOB zero fill == conv zero padding) and the [BN x 64]
 //                              slices of the pointwise weights (128B-swizzled, K-major); when the whole weight
 //                              matrix fits it is loaded once and stays resident
-//   warps 0-7   depthwise    : lane = channel pair, 4x4 output pixels per warp, FHFMA (16-bit x 16-bit + fp32,
-//                              exact products) -> BN affine -> act -> 16-bit, written straight into the
+//   warps 0-7   depthwise    : lane = channel pair, 4x4 output pixels per warp; 3x3: FFMA2 on fp32 pairs widened once,
+//                              5x5: FHFMA (16-bit x 16-bit + fp32) -- exact products, fp32 accumulation either way ->
+//                              BN affine (FFMA2) -> act folded into the 16-bit conversion -> written straight into the
 //                              128B-swizzled K-major A operand tile in shared memory (never touches HBM)
-//   warp 17     MMA issuer   : tcgen05.mma.cta_group::1.kind::f16, M=128, N<=256, K=16, fp32 accumulators in
-//                              TMEM (double-buffered so the next item's MMAs overlap this item's epilogue)
-//   warps 8-15  epilogue     : tcgen05.ld 32x32b -> BN affine + act -> 16-bit -> global (x4 replicated + skip
-//                              for decoder blocks; or the folded 1-channel head)
+//   warp 17     MMA issuer   : tcgen05.mma.cta_group::1.kind::f16, M=128, N<=256 per instruction, K=16, fp32 accumulators
+//                              in TMEM: two of <= 256 columns (the next item's MMAs overlap this item's drain) or one
+//                              of up to 512 (a whole 512-channel output tile as ONE item)
+//   warps 8-15  epilogue     : tcgen05.ld 32x32b -> BN affine + act -> 16-bit -> staging tile -> TMA tensor stores (x4
+//                              strided views for the nearest-x2 upsample, reduce-add into the skip tensor; or the folded
+//                              1-channel head).  Two groups of four warps: alternate items, or alternate 64-column blocks
+//                              of every item, or all eight warps on one staging tile (see TcParams)
 // mbarrier rings: input stages (TMA -> dw), A stages (dw -> MMA), B stages (TMA -> MMA), accumulators
 // (MMA -> epilogue).
 #include <cuda.h>
