@@ -36,7 +36,7 @@ struct StemParams {
     int tmem_cols;
     unsigned long long mg_tx, mg_ty;
     void* out;
-    const float2* affine;    // [n_pad] (scale/6, bias/6)
+    const float2* affine;    // [n_pad / 2] x (scale, scale, bias, bias) of a channel pair
 };
 
 struct StemBarriers {
