@@ -701,6 +701,7 @@ int fd_debug_block_plan(int ksize, int stride, int h_out, int w_out, int n, int 
                        q.n_stg, q.smem_bytes, q.tmem_cols, q.in_stage_stride};
     for (int i = 0; i < 16; ++i) out[i] = v[i];
     if (cap >= 18) { out[16] = q.nacc; out[17] = q.epi_colsplit; }
+    if (cap >= 19) out[18] = q.epi_wide;
     return FD_OK;
 }
 

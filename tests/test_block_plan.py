@@ -8,14 +8,14 @@ import pytest
 from fastdepth_b200 import _lib, synthetic
 
 KEYS = ('ok', 'splits', 'n_cta', 'items', 'kblocks', 's_in', 's_a', 's_b', 'bn', 'nb', 'b_resident', 'epi_groups',
-        'n_stg', 'smem_bytes', 'tmem_cols', 'in_stage_stride', 'nacc', 'epi_colsplit')
+        'n_stg', 'smem_bytes', 'tmem_cols', 'in_stage_stride', 'nacc', 'epi_colsplit', 'epi_wide')
 STRIDES = (2, 1, 2, 1, 2, 1, 2, 1, 1, 1, 1, 1, 2, 1)
 
 
 def plan(ks, stride, h, w, n, cin, cout, head=0):
     lib = _lib.load()
-    out = (ctypes.c_int * 18)()
-    _lib.check(lib.fd_debug_block_plan(ks, stride, h, w, n, cin, cout, head, out, 18))
+    out = (ctypes.c_int * 19)()
+    _lib.check(lib.fd_debug_block_plan(ks, stride, h, w, n, cin, cout, head, out, 19))
     return dict(zip(KEYS, out))
 
 
@@ -59,3 +59,40 @@ def test_stock_b64_plans_snapshot(built_lib):
     assert p['splits'] == 1 and p['n_cta'] == 512 and p['nacc'] == 1 and p['bn'] == 256 and p['epi_colsplit'] == 1
     p = plan(5, 1, 112, 112, 64, 64, 32, head=1)  # decode_conv5 + folded head
     assert p['n_stg'] == 0 and p['splits'] == 1
+
+
+def test_planner_invariants_on_random_blocks(built_lib):
+    """Property test: ANY block the fused kernel may be asked to run gets a plan that honours the kernel's assumptions
+    (the assumptions are the ones block_tc_kernel relies on without checking)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=400, deadline=None)
+    @given(ks_stride=st.sampled_from([(3, 1), (3, 2), (5, 1)]), cin=st.integers(1, 160).map(lambda v: 8 * v),
+           cout=st.integers(1, 160).map(lambda v: 8 * v), hw=st.sampled_from([(7, 7), (14, 14), (28, 28), (56, 56), (112, 112), (15, 20), (30, 40), (3, 2)]),
+           n=st.sampled_from([1, 2, 3, 16, 64, 200]), head=st.booleans())
+    def check(ks_stride, cin, cout, hw, n, head):
+        ks, stride = ks_stride
+        if head and cout > 64:
+            head = False                                   # the folded head needs the whole block in one item of <= 64 channels
+        p = plan(ks, stride, hw[0], hw[1], n, cin, cout, int(head))
+        ctx = (ks, stride, cin, cout, hw, n, head, p)
+        assert p['ok'] == 1, ctx
+        assert p['smem_bytes'] <= 227 * 1024, ctx
+        assert p['n_cta'] % 16 == 0 and p['n_cta'] * p['splits'] >= cout, ctx
+        assert p['splits'] == 1 or p['n_cta'] % 64 == 0, ctx                       # a TMA store box must not reach into the next split
+        assert p['nacc'] in (1, 2) and p['nacc'] * p['n_cta'] <= p['tmem_cols'] <= 512, ctx
+        assert p['tmem_cols'] >= 32 and p['tmem_cols'] & (p['tmem_cols'] - 1) == 0, ctx
+        assert p['bn'] % 16 == 0 and p['bn'] <= 256 and p['bn'] * p['nb'] >= p['n_cta'] > p['bn'] * (p['nb'] - 1), ctx
+        assert p['kblocks'] == (cin + 63) // 64 and 2 <= p['s_a'] <= 4 and 1 <= p['s_in'] <= 6, ctx
+        assert p['s_in'] >= 2 or (p['kblocks'] == 1 and p['items'] <= 148), ctx
+        assert 1 <= p['s_b'] <= 16 and (not p['b_resident'] or p['s_b'] == p['kblocks'] * p['nb']), ctx
+        assert p['epi_groups'] in (1, 2), ctx
+        if head:
+            assert p['n_stg'] == 0 and p['splits'] == 1 and not p['epi_colsplit'] and not p['epi_wide'], ctx
+        else:
+            assert p['n_stg'] in (p['epi_groups'], 2 * p['epi_groups']), ctx
+            assert not p['epi_colsplit'] or (p['epi_groups'] == 2 and p['n_cta'] > 64), ctx
+            assert not p['epi_wide'] or p['epi_groups'] == 1, ctx
+            assert p['nacc'] == 2 or p['epi_colsplit'], ctx                        # one accumulator: both groups must drain it
+
+    check()
