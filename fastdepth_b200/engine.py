@@ -77,8 +77,12 @@ class SkipAddEngine:
         p = self.plans.get(key)
         if p is None:
             p = _plan.Plan.from_module(m, n, h, w, x.dtype, x.device.index)
-            for k, v in self.options.items():
-                p.set_option(k, v)
+            try:
+                for k, v in self.options.items():
+                    p.set_option(k, v)
+            except Exception:
+                p.close()                      # an option stored before any plan existed turned out to be invalid
+                raise
             self.plans[key] = p
         return p
 
