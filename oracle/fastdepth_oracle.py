@@ -19,7 +19,9 @@ PINNED against the live reference module imported read-only from /root/reference
 ``tests/test_oracle.py`` checks this file against them.  (The reference itself has no
 tests or golden vectors for this path -- SURVEY.md section 4 / 8c.)
 
-Run with ``dtype=torch.float64`` for a tie-breaking higher-precision answer.
+Run with ``dtype=torch.float64`` for a tie-breaking higher-precision answer.  An operator-library-free twin of this
+file (plain C loops + numpy/ctypes composition) lives in ``oracle/fastdepth_oracle.c`` / ``oracle/c_oracle.py`` and is
+pinned against the same golden vectors.
 """
 import math
 
