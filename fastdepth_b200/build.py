@@ -1,4 +1,4 @@
-"""In-tree build of libfastdepth_b200.so (sm_100a only) and of the C oracle helper.
+"""In-tree build of libfastdepth_b200.so (sm_100a only).
 
 ``python -m fastdepth_b200.build`` or ``__graft_entry__.build()``.  nvcc cross-compiles
 without a GPU; the resulting .so is git-ignored but travels with the gpurun snapshot.
@@ -56,21 +56,5 @@ def build(force=False, verbose=False):
     return LIB
 
 
-ORACLE_SRC = os.path.join(os.path.dirname(HERE), 'oracle', 'fastdepth_oracle.c')
-ORACLE_LIB = os.path.join(os.path.dirname(HERE), 'oracle', 'libfastdepth_oracle.so')
-
-
-def build_oracle(force=False):
-    """gcc build of the plain-C oracle primitives (test infrastructure: building the checker is not using it)."""
-    if not force and not _stale(ORACLE_LIB, [ORACLE_SRC]):
-        return ORACLE_LIB
-    cmd = [os.environ.get('CC', 'gcc'), '-O2', '-fPIC', '-shared', '-o', ORACLE_LIB, ORACLE_SRC, '-lm']
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if r.returncode != 0:
-        raise RuntimeError('oracle build failed: %s\n%s' % (' '.join(cmd), r.stdout))
-    return ORACLE_LIB
-
-
 if __name__ == '__main__':
     print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
-    print(build_oracle(force='--force' in sys.argv))

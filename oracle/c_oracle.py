@@ -22,7 +22,7 @@ def load():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise RuntimeError('oracle/libfastdepth_oracle.so is missing: run `python -m fastdepth_b200.build`')
+            raise RuntimeError('oracle/libfastdepth_oracle.so is missing: run `python oracle/build_oracle.py`')
         lib = ctypes.CDLL(LIB_PATH)
         i = ctypes.c_int
         lib.fo_conv_dense.argtypes = [_F, _F, _F, i, i, i, i, i, i, i, i]

@@ -14,7 +14,7 @@
  * Tensors are contiguous NCHW float32 like the reference's; sums are accumulated in double (the reference's fp32 sum
  * order is an implementation detail of its BLAS; double is the order-independent answer to ~1e-7).
  * Composition into the network: oracle/c_oracle.py.  Pinned against the golden vectors produced by the live reference
- * (tests/test_oracle.py::test_c_oracle_*).  Built by fastdepth_b200/build.py (gcc -O2 -shared). */
+ * (tests/test_oracle.py::test_c_oracle_*).  Built by oracle/build_oracle.py (gcc -O2 -shared), which __graft_entry__.build() calls. */
 #include <math.h>
 #include <stddef.h>
 

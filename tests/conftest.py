@@ -17,7 +17,8 @@ def pytest_configure(config):
 def built_lib():
     """The in-tree shared library (built on demand; nvcc cross-compiles without a GPU)."""
     from fastdepth_b200 import build
-    build.build_oracle()                      # the plain-C oracle primitives ride along (gcc, test infrastructure)
+    from oracle import build_oracle
+    build_oracle.build()                      # the plain-C oracle primitives ride along (gcc, test infrastructure)
     return build.build()
 
 
