@@ -129,6 +129,8 @@ inline BlockPlanOut plan_block(const BlockPlanIn& q) {
             if (sp == 1 && n_cta - 64 >= cout_pad) continue;         // same plan as the next smaller candidate
             if (q.max_n_cta > 0 && nc > q.max_n_cta && !(sp == 1 && cout_pad <= 256)) continue;
             const long items = (long)q.n_tiles * sp;
+            // one accumulator cannot overlap an item's MMAs with the previous item's drain: only where every CTA has one item
+            if (nc > 256 && items > 148) continue;
             const long rounds = (items + 147) / 148;
             const long active = items < 148 ? items : 148;
             const long mma_c = 2L * nc;                              // 128 x nc x 64 MACs at 4096 MAC/clk

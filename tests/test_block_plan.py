@@ -94,5 +94,6 @@ def test_planner_invariants_on_random_blocks(built_lib):
             assert not p['epi_colsplit'] or (p['epi_groups'] == 2 and p['n_cta'] > 64), ctx
             assert not p['epi_wide'] or p['epi_groups'] == 1, ctx
             assert p['nacc'] == 2 or p['epi_colsplit'], ctx                        # one accumulator: both groups must drain it
+        assert p['nacc'] == 2 or p['items'] <= 148, ctx                            # ... and no CTA runs two items on it
 
     check()
