@@ -15,6 +15,12 @@ rank keeps 64 images).  Prints ONE JSON line on rank 0.
              (each kernel timed alone with CUDA events, L2 flushed between launches)
   cpu_baseline  the oracle port of the reference forward (torch CPU fp32) on this box's host cores,
              bounded sample
+  gpu_library_baseline  (N=1) the reference's own eager CUDA forward -- the module's nn.Conv2d / BatchNorm2d / ReLU6 /
+             F.interpolate children run by PyTorch + cuDNN (cudnn.benchmark=True), fp16 and fp32, NCHW and channels_last --
+             on the same B200: the existing-Blackwell-library bar.  Outside the product's timed region.
+  eval       BASELINE config 4's shape: bf16, 64 images per rank, per-image metrics on device, ONE all-reduce(SUM) of
+             11 doubles (NCCL under torchrun); prints delta1 / RMSE next to the oracle's, the all-reduce time and whether
+             the N-rank sums equal the sums of a single rank that ran every image (bit for bit, fp64)
   --impl reference : times ONLY that CPU implementation (the reference is pure Python on PyTorch;
              /root/reference does not exist on the GPU box, so the oracle port stands in).
 """
@@ -51,15 +57,79 @@ def parse():
     ap.add_argument('--graph', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--stage-iters', type=int, default=10)
+    ap.add_argument('--no-lib-baseline', action='store_true', help='skip the cuDNN-eager leg')
+    ap.add_argument('--no-eval', action='store_true', help='skip the bf16 sharded-evaluation leg (config 4)')
+    ap.add_argument('--e2e-steps', type=int, default=200)
     return ap.parse_args()
 
 
 def peaks():
+    """(HBM GB/s, sustained dense 16-bit TFLOP/s, SM MHz, source)"""
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs, burst copy)'
-    return 6650.0, 'fallback (B200_PROFILING.md)'
+        return (float(d['hbm_gbs']), float(d.get('bf16_tflops_sustained', 1467.7)), float(d.get('sm_max_mhz', 1965.0)),
+                'measured (MEASURED_PEAKS.json hbm_gbs burst copy; bf16_tflops_sustained)')
+    return 6650.0, 1400.0, 1965.0, 'fallback (B200_PROFILING.md)'
+
+
+NOMINAL_HBM_GBS = 8000.0        # the figure north_star quotes
+
+
+def eager_reference_forward(model, x):
+    """The reference forward (models.py:706-732) run by PyTorch's own operators on the module's children: the
+    existing-library baseline (cuDNN convolutions, ~122 kernel launches per forward).  Bench-only; the product's
+    ``forward`` never takes this route."""
+    import torch.nn.functional as F
+    keep = {}
+    for i in range(14):
+        x = getattr(model, 'conv%d' % i)(x)
+        if i in (1, 3, 5):
+            keep[i] = x
+    add_after = {4: 1, 3: 3, 2: 5}
+    for j in range(1, 6):
+        x = getattr(model, 'decode_conv%d' % j)(x)
+        x = F.interpolate(x, scale_factor=2, mode='nearest')
+        if j in add_after:
+            x = x + keep[add_after[j]]
+    return model.decode_conv6(x)
+
+
+def gpu_library_baseline(widths, sd, n, h, w, dev, ours_value, iters=20):
+    """img/s of the eager cuDNN forward at batch n for {fp16, fp32} x {NCHW, channels_last}; CUDA events, synchronised."""
+    import models
+    from fastdepth_b200 import synthetic
+    prev = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True                      # reference main.py:10
+    out = {'batch': n, 'api': 'torch %s eager / cuDNN %s, cudnn.benchmark=True' % (torch.__version__, torch.backends.cudnn.version())}
+    x32 = synthetic.synthetic_input(n, h, w, seed=0).to(dev)
+    try:
+        for dname, dt in (('fp16', torch.float16), ('fp32', torch.float32)):
+            for lname, fmt in (('nchw', torch.contiguous_format), ('channels_last', torch.channels_last)):
+                m = models.MobileNetSkipAdd((h, w), pretrained=False, widths=widths)
+                m.load_state_dict(sd)
+                m = m.eval().to(dev).to(dt).to(memory_format=fmt)
+                x = x32.to(dt).contiguous(memory_format=fmt)
+                with torch.no_grad():
+                    for _ in range(5):
+                        y = eager_reference_forward(m, x)
+                    torch.cuda.synchronize(dev)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(iters):
+                        y = eager_reference_forward(m, x)
+                    e1.record()
+                    torch.cuda.synchronize(dev)
+                out['%s_%s' % (dname, lname)] = n * iters / (e0.elapsed_time(e1) * 1e-3)
+                del m, y
+    finally:
+        torch.backends.cudnn.benchmark = prev
+    best16 = max(out['fp16_nchw'], out['fp16_channels_last'])
+    out.update({'unit': UNIT, 'best_fp16': best16, 'ours_over_best_fp16': ours_value / best16,
+                'ours_over_fp32_nchw': ours_value / out['fp32_nchw'],
+                'note': 'reference forward (models.py:706-732) through PyTorch eager on the same GPU; fp32 NCHW is what '
+                        'main.py feeds (main.py:68), fp16 is the like-for-like precision of `value`'})
+    return out
 
 
 class ClockSampler(threading.Thread):
@@ -177,6 +247,74 @@ def cpu_forward_rate(sd, h, w, budget_s, min_steps, warmup, batch=None):
     return batch / per, batch, len(times), per
 
 
+def run_eval(rank, world, dev, widths, sd, h, w, n):
+    """BASELINE config 4's shape on however many ranks there are: bf16, n images per rank, image-sharded, per-image
+    metrics on device, ONE all-reduce(SUM) of 11 doubles (reference metrics.py:71-95, main.py:80-82).  Returns rank 0's
+    report.  Outside every timed region of the headline metric; the oracle is used here as the checker only (targets
+    around its fp32 prediction, SURVEY.md 8d, and its own per-image metrics on the same pairs)."""
+    import torch.distributed as dist
+    import models
+    from fastdepth_b200 import evaluate, synthetic
+    from fastdepth_b200.plan import METRIC_NAMES, metrics_accumulate
+    from oracle import fastdepth_oracle as orc           # checker only
+    dt = torch.bfloat16
+    torch.set_grad_enabled(False)
+    m = models.MobileNetSkipAdd((h, w), pretrained=False, widths=widths)
+    m.load_state_dict(sd)
+    m = m.eval().to(dev).to(dt)
+    x = synthetic.synthetic_input(n, h, w, seed=5000 + rank)
+    torch.set_num_threads(max(1, min(32, usable_cpus() // max(1, world))))
+    ref = orc.skipadd_forward(sd, x)
+    tgt = synthetic.synthetic_target(ref, seed=6000 + rank)
+    xd, td = x.to(dev).to(dt), tgt.to(dev)
+    # (a) the sharded evaluation through the product's own entry point (forward + device metrics + the one collective)
+    ours, sums = evaluate.evaluate(m, [(xd[:n // 2], td[:n // 2]), (xd[n // 2:], td[n // 2:])], dev, return_sums=True)
+    # (b) the collective alone, timed on the device: 11 doubles, latency only
+    ar_us = None
+    if world > 1:
+        scratch = torch.ones(11, dtype=torch.float64, device=dev)
+        for _ in range(10):
+            dist.all_reduce(scratch)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            dist.all_reduce(scratch)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1) / 50 * 1e3], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ar_us = t.item()
+    # (c) the oracle's metrics on the same (image, target) pairs, reduced the same way
+    om, cnt = orc.average_per_image(ref.numpy(), tgt.numpy())
+    osum = torch.tensor([om[k] * cnt for k in METRIC_NAMES] + [float(cnt)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(osum)
+    oracle_avg = {k: osum[i].item() / osum[-1].item() for i, k in enumerate(METRIC_NAMES)}
+    # (d) bookkeeping: ONE rank runs every rank's images; its fp64 sums must equal the all-reduced ones bit for bit
+    if world > 1:
+        xs_all = [torch.empty_like(xd) for _ in range(world)]
+        ts_all = [torch.empty_like(td) for _ in range(world)]
+        dist.all_gather(xs_all, xd)
+        dist.all_gather(ts_all, td)
+    else:
+        xs_all, ts_all = [xd], [td]
+    same = None
+    if rank == 0:
+        one = evaluate.new_sums(dev)
+        for xa, ta in zip(xs_all, ts_all):
+            metrics_accumulate(m(xa), ta, one)
+        torch.cuda.synchronize(dev)
+        same = bool(torch.equal(one, sums))
+    del m
+    return {'config': 'BASELINE config 4 shape: bf16, %d images per rank x %d rank(s) = %d, image-sharded' % (n, world, n * world),
+            'dtype': 'bf16', 'images': int(round(ours['count'])), 'delta1': ours['delta1'], 'rmse_mm': ours['rmse'],
+            'absrel': ours['absrel'], 'delta1_oracle_fp32': oracle_avg['delta1'], 'rmse_mm_oracle_fp32': oracle_avg['rmse'],
+            'absrel_oracle_fp32': oracle_avg['absrel'],
+            'collective': ('NCCL all_reduce(SUM) of 11 fp64 (88 B), %d ranks' % world) if world > 1 else 'none (1 rank)',
+            'allreduce_us': ar_us, 'n_rank_sums_equal_single_rank_sums_bitwise': same}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -272,7 +410,7 @@ def main():
     # synchronisations (the work spans three streams), max over ranks.
     xh = [x.cpu().pin_memory() for x in xs[:3]]
     yh = [torch.empty((n, 1, h, w), dtype=dtype).pin_memory() for _ in range(3)]
-    e2e_steps = max(6, args.steps)
+    e2e_steps = max(6, args.steps, args.e2e_steps)      # ~0.13 s per repeat at batch 64: long enough to be stable
 
     def run_pipeline(k):
         tickets = []
@@ -283,21 +421,29 @@ def main():
         for t in tickets[-2:]:
             plan.pipeline_wait(t)
 
-    run_pipeline(4)
-    barrier()
-    t0 = time.perf_counter()
-    run_pipeline(e2e_steps)
-    torch.cuda.synchronize(dev)
-    el = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(el, op=dist.ReduceOp.MAX)
-    ms_e2e = el.item() * 1e3
+    run_pipeline(8)
+    reps = []
+    for _ in range(3):                                    # median of three repeats (max over ranks each)
+        barrier()
+        t0 = time.perf_counter()
+        run_pipeline(e2e_steps)
+        torch.cuda.synchronize(dev)
+        el = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        reps.append(el.item() * 1e3)
+    ms_e2e = sorted(reps)[1]
     # the plain synchronous call, for reference
     ms_sync = timed(lambda i: plan.forward_host(xh[i % 3], yh[i % 3], sp), 5, 2) / 5
     clocks = sampler.summary() if sampler else None
 
     value = world * n * args.steps / (ms_total * 1e-3)
     e2e_value = world * n * e2e_steps / (ms_e2e * 1e-3)
+
+    # ---- config-4 evaluation leg: every rank takes part (forward in bf16, device metrics, the path's one collective)
+    eval_info = None
+    if not args.no_eval and (h, w) == (224, 224):
+        eval_info = run_eval(rank, world, dev, widths, sd, h, w, n)
 
     if rank != 0:
         if world > 1:
@@ -306,16 +452,25 @@ def main():
         return
 
     # ---- per-kernel roofline (rank 0, each kernel alone, L2 flushed) ---------------------------
-    hbm_peak, peak_src = peaks()
+    hbm_peak, tensor_peak, sm_mhz, peak_src = peaks()
+    n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
     steps = plan.time_steps(xs[0], y, sp, warmup=2, iters=args.stage_iters, flush_l2=True)
     for s in steps:
         s['gbs'] = s['alg_bytes'] / (s['ms'] * 1e-3) / 1e9 if s['ms'] > 0 else 0.0
         s['frac'] = s['gbs'] / hbm_peak
         s['tflops'] = 2 * s['macs'] / (s['ms'] * 1e-3) / 1e12 if s['ms'] > 0 else 0.0
+        # the three floors of a fused stage: HBM (algorithmic bytes), the SIMT FMA pipe for the depthwise taps (128 FMA lanes
+        # per SM and clock, north_star keeps them off the tensor cores) and the tensor pipe for the dense contraction
+        s['hbm_floor_us'] = s['alg_bytes'] / (hbm_peak * 1e9) * 1e6
+        s['fma_floor_us'] = s['dw_macs'] / (n_sms * 128.0 * sm_mhz * 1e6) * 1e6
+        s['tensor_floor_us'] = 2 * s['dense_macs'] / (tensor_peak * 1e12) * 1e6
+        s['floor_us'] = max(s['hbm_floor_us'], s['fma_floor_us'], s['tensor_floor_us'])
     top = max(steps, key=lambda s: s['ms'])
     # DRAM traffic of that kernel from the committed `ncu --set full` capture of the same configuration (if any)
     traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'r01_final_traffic.json')
+    tpath = os.path.join(ROOT, 'profiles', 'r02_final_traffic.json')
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, 'profiles', 'r01_final_traffic.json')
     if os.path.exists(tpath) and args.widths == 'stock' and args.dtype == 'fp16' and n == 64 and (h, w) == (224, 224) and args.path == 1:
         tj = json.load(open(tpath))['stages'].get(top['stage_name'])
         if tj:
@@ -334,6 +489,10 @@ def main():
     tgt = synthetic.synthetic_target(want, seed=1)
     m_ours, _ = orc.average_per_image(got.numpy(), tgt.numpy())
     m_ref, _ = orc.average_per_image(want.numpy(), tgt.numpy())
+
+    lib = None
+    if not args.no_lib_baseline and world == 1 and args.dtype == 'fp16':
+        lib = gpu_library_baseline(widths, sd, n, h, w, dev, value)
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -357,21 +516,39 @@ def main():
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': xh[0].numel() * xh[0].element_size(),
                 'd2h_bytes_per_step': yh[0].numel() * yh[0].element_size(), 'ms_per_step': ms_e2e / e2e_steps,
                 'api': 'fd_pipeline_submit/fd_pipeline_wait (C-ABI, pinned host buffers, 3 batches in flight)',
+                'steps': e2e_steps, 'repeats_ms': [round(r, 3) for r in reps], 'statistic': 'median of 3 repeats, max over ranks each',
                 'sync_call_ms_per_step': ms_sync, 'sync_call_api': 'fd_forward_host'},
         'gpu_launches': plan.launches_per_forward() * args.steps,
         'launches_per_step': plan.launches_per_forward(),
         'clocks': clocks,
         'roofline': {'bound': 'hbm', 'achieved': top['gbs'], 'peak': hbm_peak, 'unit': 'GB/s', 'frac': top['frac'],
-                     'traffic': traffic, 'kernel': top['kernel'], 'stage': top['stage_name'], 'peak_source': peak_src,
+                     'frac_nominal_8tbs': top['gbs'] / NOMINAL_HBM_GBS,
+                     'traffic': traffic, 'traffic_source': os.path.basename(tpath) if traffic else None,
+                     'kernel': top['kernel'], 'stage': top['stage_name'], 'peak_source': peak_src,
                      'kernel_ms': top['ms'], 'share_of_step': top['ms'] / sum_ms,
+                     'alg_bytes': top['alg_bytes'],
+                     # a fused depthwise stage also has a SIMT floor: taps / (128 FMA lanes x SMs x clock); when that exceeds
+                     # the HBM time the HBM fraction of even a perfect kernel is hbm_floor / fma_floor
+                     'hbm_floor_us': top['hbm_floor_us'], 'fma_floor_us': top['fma_floor_us'],
+                     'tensor_floor_us': top['tensor_floor_us'],
+                     'frac_ceiling_given_fma_floor': min(1.0, top['hbm_floor_us'] / max(top['floor_us'], 1e-9)),
+                     'frac_of_binding_floor': top['floor_us'] / (top['ms'] * 1e3),
                      'whole_step': {'alg_bytes': alg_total, 'gbs_at_value': alg_total / (ms_total / args.steps * 1e-3) / 1e9,
-                                    'frac_at_value': alg_total / (ms_total / args.steps * 1e-3) / 1e9 / hbm_peak}},
+                                    'frac_at_value': alg_total / (ms_total / args.steps * 1e-3) / 1e9 / hbm_peak,
+                                    'frac_nominal_8tbs': alg_total / (ms_total / args.steps * 1e-3) / 1e9 / NOMINAL_HBM_GBS,
+                                    'sum_of_isolated_kernel_ms': sum_ms,
+                                    'sum_of_binding_floors_us': sum(s['floor_us'] for s in steps)}},
         'stages': [{'stage': s['stage_name'], 'kernel': s['kernel'], 'ms': round(s['ms'], 5),
                     'alg_mb': round(s['alg_bytes'] / 1e6, 3), 'gbs': round(s['gbs'], 1), 'frac': round(s['frac'], 4),
-                    'tflops': round(s['tflops'], 2)} for s in steps],
+                    'frac_8tbs': round(s['gbs'] / NOMINAL_HBM_GBS, 4), 'tflops': round(s['tflops'], 2),
+                    'hbm_floor_us': round(s['hbm_floor_us'], 2), 'fma_floor_us': round(s['fma_floor_us'], 2),
+                    'tensor_floor_us': round(s['tensor_floor_us'], 2),
+                    'frac_of_floor': round(s['floor_us'] / (s['ms'] * 1e3), 4) if s['ms'] > 0 else 0.0} for s in steps],
         'parity': {'max_rel_err_vs_oracle': max_rel, 'delta1': m_ours['delta1'], 'delta1_oracle': m_ref['delta1'],
                    'rmse_mm': m_ours['rmse'], 'rmse_mm_oracle': m_ref['rmse']},
         'cpu_baseline': cpu,
+        'gpu_library_baseline': lib,
+        'eval': eval_info,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -46,6 +46,7 @@ SIGNATURES = {
     'fd_plan_step_count': (ctypes.c_int, [_vp, _c_int_p]),
     'fd_plan_step_info': (ctypes.c_int, [_vp, ctypes.c_int, _c_int_p, _c_double_p, _c_double_p,
                                          ctypes.c_char_p, ctypes.c_int]),
+    'fd_plan_step_macs': (ctypes.c_int, [_vp, ctypes.c_int, _c_double_p, _c_double_p]),
     'fd_plan_time_steps': (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_float_p]),
     'fd_plan_trace_stage': (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int,
                                            _c_int_p, _c_int_p]),

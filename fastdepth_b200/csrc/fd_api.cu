@@ -11,8 +11,6 @@
 
 namespace fd {
 
-extern int g_use_pdl;
-extern int g_wait_sleep_ns;
 BlockPlanOut block_tc_debug_plan(int ksize, int stride, int h_out, int w_out, int n, int c_in, int c_out, int head);
 
 // ---- error state -----------------------------------------------------------------------
@@ -37,7 +35,7 @@ int launch_nyu_val_gather(int dtype, const uint8_t* rgb, const float* depth, con
 struct BlockTcPlan;   // opaque per-stage state (tensor maps, tile config)
 bool block_tc_supported(int dtype, const StageGeom& g, bool head_fused);
 int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float head_scale, float head_bias, int head_act,
-                     void* head_out, bool tma_epilogue, BlockTcPlan** out);
+                     void* head_out, bool tma_epilogue, const TcLaunchOpts& opts, BlockTcPlan** out);
 int block_tc_launch(BlockTcPlan* p, cudaStream_t st, void* head_out);
 void block_tc_destroy(BlockTcPlan* p);
 const char* block_tc_name(BlockTcPlan* p);
@@ -46,7 +44,7 @@ int block_tc_trace(BlockTcPlan* bp, cudaStream_t st, void* head_out, unsigned lo
 struct StemTcPlan;
 bool stem_tc_supported(int dtype, const StageGeom& g);
 int stem_tc_prepare(int dtype, const StageGeom& g, const float* w27_dev, const float* scale_dev, const float* bias_dev, void* out,
-                    StemTcPlan** res);
+                    const TcLaunchOpts& opts, StemTcPlan** res);
 int stem_tc_launch(StemTcPlan* sp, const void* x, cudaStream_t st);
 void stem_tc_destroy(StemTcPlan* sp);
 const char* stem_tc_name(StemTcPlan* sp);
@@ -81,6 +79,7 @@ struct Step {
     int stage;
     std::string name;
     double alg_bytes, macs;
+    double dw_macs = 0.0;                // of which depthwise (SIMT FMA pipe); the rest is the dense contraction (tensor pipe)
     std::function<int(cudaStream_t, const void*, void*)> run;
 };
 
@@ -89,7 +88,7 @@ struct Step {
 using namespace fd;
 
 struct fd_plan {
-    int n = 0, h = 0, w = 0, dtype = 0, device = 0;
+    int n = 0, h = 0, w = 0, dtype = 0, device = 0, n_sms = 148;
     std::vector<Stage> stages;
     std::vector<Step> steps;
     bool steps_valid = false;
@@ -109,6 +108,7 @@ struct fd_plan {
     struct GraphEntry { const void* x; void* y; cudaGraphExec_t exec; unsigned long long stamp; };
     std::vector<GraphEntry> graphs;
     unsigned long long graph_clock = 0;
+    int graph_misses = 0;                // consecutive fd_forward calls that found no captured graph for their (x, y) pair
 };
 static const size_t kMaxGraphs = 8;
 
@@ -168,6 +168,8 @@ static int build_steps(fd_plan* p) {
     for (auto& s : p->stages)
         if (!s.have_weights) return fail(FD_ERR_STATE, "fd_plan_set_stage_weights was not called for every stage");
 
+    TcLaunchOpts lopts;                   // every kernel plan keeps its own copy (no process-wide launch state)
+    lopts.pdl = p->opt_pdl; lopts.sleep_ns = p->opt_wait_sleep_ns; lopts.n_sms = p->n_sms;
     Stage& head = p->stages[ns - 1];
     Stage& last = p->stages[ns - 2];
     // decode_conv6 below the last upsample: exact because a 1x1 conv, a per-channel affine and ReLU
@@ -192,7 +194,7 @@ static int build_steps(fd_plan* p) {
             Stage* sp = &s;
             const int dtype = p->dtype;
             if (p->opt_path == 1 && stem_tc_supported(dtype, s.g)) {
-                int rc = stem_tc_prepare(dtype, s.g, s.pw_w_f32, s.pw_scale, s.pw_bias, s.out, &s.stc);
+                int rc = stem_tc_prepare(dtype, s.g, s.pw_w_f32, s.pw_scale, s.pw_bias, s.out, lopts, &s.stc);
                 if (rc != FD_OK) return rc;
                 st.name = stem_tc_name(s.stc);
                 StemTcPlan* stc = s.stc;
@@ -228,13 +230,14 @@ static int build_steps(fd_plan* p) {
                 // block's output and the skip never has to be read by the SM
                 const bool tma_epi = p->opt_tma_epilogue != 0;
                 if (tma_epi && p->opt_inplace_skip && a.skip != nullptr) { a.out = const_cast<void*>(a.skip); s.out_eff = a.out; }
-                int rc = fuse_head ? block_tc_prepare(dtype, a, head.pw_w_f32, head.head_scale, head.head_bias, head.g.act, nullptr, false, &s.tc)
-                                   : block_tc_prepare(dtype, a, nullptr, 0.f, 0.f, 0, nullptr, tma_epi && (a.skip == nullptr || a.skip == a.out), &s.tc);
+                int rc = fuse_head ? block_tc_prepare(dtype, a, head.pw_w_f32, head.head_scale, head.head_bias, head.g.act, nullptr, false, lopts, &s.tc)
+                                   : block_tc_prepare(dtype, a, nullptr, 0.f, 0.f, 0, nullptr, tma_epi && (a.skip == nullptr || a.skip == a.out), lopts, &s.tc);
                 if (rc != FD_OK) return rc;
                 Step st;
                 st.stage = i;
                 st.name = block_tc_name(s.tc);
                 st.macs = dw_macs + pw_macs + (fuse_head ? px_out * s.g.c_out : 0.0);
+                st.dw_macs = dw_macs;
                 st.alg_bytes = fuse_head ? (px_in * s.g.c_in + px_out * 4.0) * es + w_bytes + s.g.c_out * 4.0 : fused_bytes;
                 BlockTcPlan* tc = s.tc;
                 st.run = [tc](cudaStream_t stream, const void*, void* y) { return block_tc_launch(tc, stream, y); };
@@ -245,6 +248,7 @@ static int build_steps(fd_plan* p) {
                 d.stage = i;
                 d.name = s.g.ksize == 3 ? "dw_kernel<3>" : "dw_kernel<5>";
                 d.macs = dw_macs;
+                d.dw_macs = dw_macs;
                 d.alg_bytes = (px_in + px_out) * s.g.c_in * es + (double)s.g.c_in * (s.g.ksize * s.g.ksize + 2) * 4;
                 d.run = [a, dtype](cudaStream_t stream, const void*, void*) { return launch_dw(dtype, a, stream); };
                 p->steps.push_back(d);
@@ -281,8 +285,6 @@ static int build_steps(fd_plan* p) {
 }
 
 static int run_steps(fd_plan* p, const void* x, void* y, cudaStream_t st) {
-    g_use_pdl = p->opt_pdl;
-    g_wait_sleep_ns = p->opt_wait_sleep_ns;
     for (auto& s : p->steps) {
         int rc = s.run(st, x, y);
         if (rc != FD_OK) return rc;
@@ -318,7 +320,7 @@ int fd_plan_create(const fd_stage_desc* stages, int n_stages, int n, int h, int 
     if (!guard.ok) return fail(FD_ERR_CUDA, "cudaSetDevice failed");
 
     fd_plan* p = new fd_plan();
-    p->n = n; p->h = h; p->w = w; p->dtype = dtype; p->device = device;
+    p->n = n; p->h = h; p->w = w; p->dtype = dtype; p->device = device; p->n_sms = prop.multiProcessorCount;
     p->stages.resize(n_stages);
     const size_t es = dtype_size(dtype);
     int ch = 3, hh = h, ww = w;
@@ -484,9 +486,17 @@ int fd_forward(fd_plan* p, const void* x_dev, void* y_dev, void* stream) {
     for (auto& g : p->graphs)
         if (g.x == x_dev && g.y == y_dev) {
             g.stamp = ++p->graph_clock;
+            p->graph_misses = 0;
             FD_CUDA_OK(cudaGraphLaunch(g.exec, st));
             return FD_OK;
         }
+    // A caller that never repeats an (x, y) pair (fresh output tensors that it keeps alive, a stream of distinct inputs) would
+    // pay a capture + instantiate + eviction per call: after two cache-fulls of consecutive misses launch directly until a
+    // pair repeats again (19 PDL-chained launches cost far less than one capture).
+    if (++p->graph_misses > 2 * (int)kMaxGraphs) {
+        if (p->graph_misses > (1 << 30)) p->graph_misses = 2 * (int)kMaxGraphs + 1;
+        return run_steps(p, x_dev, y_dev, st);
+    }
     cudaStream_t cap;
     FD_CUDA_OK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
     cudaGraph_t graph = nullptr;
@@ -644,6 +654,18 @@ int fd_plan_step_info(fd_plan* p, int step, int* stage, double* alg_bytes, doubl
         strncpy(kernel_name, s.name.c_str(), name_cap - 1);
         kernel_name[name_cap - 1] = 0;
     }
+    return FD_OK;
+}
+
+int fd_plan_step_macs(fd_plan* p, int step, double* dw_macs, double* dense_macs) {
+    if (!p) return fail(FD_ERR_INVALID, "NULL plan");
+    DeviceGuard guard(p->device);
+    int rc = ensure_steps(p);
+    if (rc) return rc;
+    if (step < 0 || step >= (int)p->steps.size()) return fail(FD_ERR_INVALID, "bad step index");
+    const Step& s = p->steps[step];
+    if (dw_macs) *dw_macs = s.dw_macs;
+    if (dense_macs) *dense_macs = s.macs - s.dw_macs;
     return FD_OK;
 }
 

@@ -18,6 +18,7 @@ struct BlockPlanIn {
     int max_n_cta;               // 0 = no limit; experiments: cap the output channels per item (FD_TC_MAX_NCTA)
     int no_wide;                 // experiments: 1 = a single epilogue group stays four warps (FD_TC_NO_WIDE)
     int no_colsplit;             // experiments: 1 = epilogue groups take alternate items even when they could share (FD_TC_NO_COLSPLIT)
+    int n_sms;                   // SMs of the device (one CTA each); 0 = 148 (B200)
 };
 struct BlockPlanOut {
     int ok;
@@ -36,6 +37,7 @@ struct BlockPlanOut {
 // single-K-block blocks want a deep A ring to hide the serial latency of the MMA issue thread).
 inline bool plan_block_smem(const BlockPlanIn& q, BlockPlanOut& p, bool allow_narrow) {
     const int splits = p.splits;
+    const int sms = q.n_sms > 0 ? q.n_sms : 148;
     const int fixed = q.barrier_bytes + 2048 + (q.head ? 3 : 2) * p.cpad_all * 4;      // 2048: two 1 KB alignment slacks
     const int total = kPlanSmemBudget - fixed;
     long best = -(1L << 60);
@@ -60,7 +62,7 @@ inline bool plan_block_smem(const BlockPlanIn& q, BlockPlanOut& p, bool allow_na
                         if (left < 0) continue;
                         int s_in = left / p.in_stage_stride;
                         if (s_in > kPlanMaxIn) s_in = kPlanMaxIn;
-                        if (s_in < 2 && !(s_in == 1 && p.kblocks == 1 && p.items <= 148)) continue;
+                        if (s_in < 2 && !(s_in == 1 && p.kblocks == 1 && p.items <= sms)) continue;
                         const int bn_eff = bn < 128 ? bn : 128;
                         // weight ring depth in K-blocks: below 2 the MMA of K-block k+1 waits for a weight load that could
                         // only start when the MMA of K-block k had finished (measured: conv7 lost a third of its time there)
@@ -98,6 +100,7 @@ inline bool plan_block_smem(const BlockPlanIn& q, BlockPlanOut& p, bool allow_na
 
 inline BlockPlanOut plan_block(const BlockPlanIn& q) {
     BlockPlanOut p{};
+    const long sms = q.n_sms > 0 ? q.n_sms : 148;
     const int NI = q.tile ? 2 : 1, TH = 8, TW = q.tile ? 8 : 16;
     const int IH = (TH - 1) * q.stride + q.ksize, IW = (TW - 1) * q.stride + q.ksize;
     p.kblocks = (q.c_in + kPlanKblk - 1) / kPlanKblk;
@@ -110,7 +113,7 @@ inline BlockPlanOut plan_block(const BlockPlanIn& q) {
     // room for two and overlaps the next item's MMAs with this item's drain), multiples of 64 when there is more than
     // one split (the epilogue moves whole [128 px][64 ch] tiles and must not touch a neighbouring split's columns).
     // Candidates are tried in the order of their modelled kernel time
-    //     rounds over the 148 SMs x K-blocks x max(depthwise, MMA, L2 -> SM operand traffic) + exposed drain of the last item
+    //     rounds over the SMs x K-blocks x max(depthwise, MMA, L2 -> SM operand traffic) + exposed drain of the last item
     // until one fits shared memory.  Per-K-block cycles are measured ones (profiles/r01_trace_*); the operand-traffic term
     // is chip-wide: the L2 delivers ~6300 B/clk to all SMs together (B300_MICROARCH.md), ~5500 sustained here, and the
     // 14x14 blocks sit on it (conv7: 148 CTAs x 57 KB per K-block every 1750 cycles).
@@ -130,9 +133,9 @@ inline BlockPlanOut plan_block(const BlockPlanIn& q) {
             if (q.max_n_cta > 0 && nc > q.max_n_cta && !(sp == 1 && cout_pad <= 256)) continue;
             const long items = (long)q.n_tiles * sp;
             // one accumulator cannot overlap an item's MMAs with the previous item's drain: only where every CTA has one item
-            if (nc > 256 && items > 148) continue;
-            const long rounds = (items + 147) / 148;
-            const long active = items < 148 ? items : 148;
+            if (nc > 256 && items > sms) continue;
+            const long rounds = (items + sms - 1) / sms;
+            const long active = items < sms ? items : sms;
             const long mma_c = 2L * nc;                              // 128 x nc x 64 MACs at 4096 MAC/clk
             const long l2_c = active * (p.in_stage_bytes + 128L * nc) / 5500;
             long kb_c = dw_c > mma_c ? dw_c : mma_c;

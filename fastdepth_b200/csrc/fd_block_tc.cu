@@ -80,7 +80,11 @@ struct TcParams {
                           //    lane quarter taking 32 of each block's 64 columns -- twice the drain rate where only one tile fits
     int epi_groups;       // 2: two groups of four epilogue warps take alternate items; 1: one group takes all (smem is tight)
     int out_pitch, skip_pitch;   // elements between pixels of the output / skip tensors (>= c_out: channel slice of a concat buffer)
-    int sleep_ns;         // > 0: latency-tolerant waits sleep this long between probes instead of spinning
+    int sleep_ns;         // > 0: latency-tolerant waits (epilogue: accumulator ready, TMA producer: stage free) back off with
+                          //      nanosleep between probes instead of re-issuing try_wait every ~27 cycles (those probes are real
+                          //      issue slots: a third of all warp instructions of decode_conv5 in the round-1 capture)
+    int mma_sleep_ns;     // same for the MMA issuer's waits (operand ready / accumulator drained)
+    int dw_sleep_ns;      // same for the depthwise warps' wait for an input stage
     int epi_tma;          // 1: staging tiles leave through TMA tensor stores (4 strided views for nearest-x2 upsampling)
     int epi_red;          // 1: ... as element-wise ADD into the skip tensor, which then IS the block's output (in place)
     unsigned long long mg_splits, mg_tx, mg_ty;   // 2^40 / d reciprocals for the item -> tile decode
@@ -122,7 +126,9 @@ __device__ __forceinline__ ItemCoord decode_item(const TcParams& p, int w, int N
         if (p.trace != nullptr && blockIdx.x == 0 && (idx) < TC_TRACE_N) p.trace[(row) * TC_TRACE_N + (idx)] = clock64(); \
     } while (0)
 
-template <typename T, int KS, int STRIDE, int NI, int TH, int TW, bool RELU6>
+// HALFK: the block has at most 32 input channels (conv1): the 16 channel pairs fill half a warp, so the two half-warps split the
+// warp's 4x4 pixel block into its upper and lower two rows instead of computing 32 zero channels each.
+template <typename T, int KS, int STRIDE, int NI, int TH, int TW, bool RELU6, bool HALFK = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w,
                 const __grid_constant__ CUtensorMap tm_o0, const __grid_constant__ CUtensorMap tm_o1,
@@ -143,10 +149,10 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
     const uint32_t in_off = b_off + p.s_b * p.b_stage_bytes;
     const uint32_t stg_off = (in_off + p.s_in * p.in_stage_stride + 1023u) & ~1023u;   // epilogue staging: [128 px][64 ch] 16-bit, SW128 atoms
     const uint32_t pw_off = stg_off + (uint32_t)p.n_stg * 16384u;
-    const uint32_t bar_off = pw_off + (p.head ? 3u : 2u) * (uint32_t)p.cpad_all * 4u;
+    const uint32_t bar_off = pw_off + (p.head ? 3u : 2u) * (uint32_t)p.cpad_all * 4u;     // (head: 16-bit weights use half of their slot)
     TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem + bar_off);
     float2* s_pw_affine = reinterpret_cast<float2*>(smem + pw_off);           // (scale, scale, bias, bias) per output-channel pair
-    float* s_head_w = reinterpret_cast<float*>(s_pw_affine + p.cpad_all);
+    uint32_t* s_head_w2 = reinterpret_cast<uint32_t*>(s_pw_affine + p.cpad_all);   // head weights of a channel pair, 16-bit x 2
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -165,7 +171,14 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
     }
     for (int i = threadIdx.x; i < p.cpad_all; i += TC_THREADS) {          // pointwise BN affine (+ head weights) -> smem
         s_pw_affine[i] = p.pw_affine[i];
-        if (p.head) s_head_w[i] = p.head_w[i];
+        if (p.head && !(i & 1)) s_head_w2[i >> 1] = MF::pack(p.head_w[i], p.head_w[i + 1]);   // cpad_all is even
+    }
+    if constexpr (HALFK) {
+        // channels 32..63 of every A row are never written by the depthwise warps: zero the stages once (their products meet
+        // the zero-filled K rows of the weights, but 0 x NaN from uninitialised shared memory would still poison the sum)
+        for (int i = threadIdx.x; i < p.s_a * (TC_A_STAGE_BYTES / 16); i += TC_THREADS)
+            reinterpret_cast<uint4*>(smem + a_off)[i] = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async();
     }
     pdl_launch_dependents();                       // the next kernel may begin its own prologue
     pdl_wait_prior_grid();                         // everything below reads what the previous kernel wrote
@@ -234,10 +247,10 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
             int tr = 0;
             bool first = true;
             for (int w = blockIdx.x; w < p.items; w += gridDim.x, racc.next((uint32_t)p.nacc), first = false) {
-                mbar_wait(bar_acc_empty + 8u * racc.s, racc.ph ^ 1u);          // epilogue has drained this accumulator
+                mbar_wait_sleep(bar_acc_empty + 8u * racc.s, racc.ph ^ 1u, (uint32_t)p.mma_sleep_ns);   // epilogue has drained this accumulator
                 const uint32_t d_tmem = tmem_base + racc.s * (uint32_t)p.n_cta;
                 for (int kb = 0; kb < p.kblocks; ++kb, ra.next((uint32_t)p.s_a)) {
-                    mbar_wait(bar_a_full + 8u * ra.s, ra.ph);
+                    mbar_wait_sleep(bar_a_full + 8u * ra.s, ra.ph, (uint32_t)p.mma_sleep_ns);
                     tc_fence_after();
                     TC_TRACE(4, tr);
                     const uint32_t a_lo = a_lo0 + ra.s * a_step;
@@ -279,7 +292,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
             for (int kb = 0; kb < p.kblocks; ++kb, rin.next((uint32_t)p.s_in), ra.next((uint32_t)p.s_a)) {
                 const uint32_t s = rin.s, ph = rin.ph, sa = ra.s, pha = ra.ph;
-                mbar_wait(smem_u32(&bars->in_full[s]), ph);
+                mbar_wait_sleep(smem_u32(&bars->in_full[s]), ph, (uint32_t)p.dw_sleep_ns);
                 if (tracer) TC_TRACE(1, tr);
                 const uint8_t* stage = smem + in_off + s * p.in_stage_stride;
                 const uint8_t* in_s = stage + in_warp_off;
@@ -297,7 +310,47 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
 #else
                 constexpr bool kDwFfma2 = KS == 3;
 #endif
-                if constexpr (kDwFfma2) {
+                if constexpr (HALFK) {
+                    static_assert(KS == 3 && STRIDE == 1, "half-K depthwise exists for the 3x3 stride-1 block only");
+                    const int hl = lane & 15, hh = lane >> 4;       // channel pair, row half of the 4x4 block
+                    const uint8_t* in_h = in_s - lane * 4 + hl * 4 + (hh * 2 * IW) * 128;
+                    const f32x2 sc2 = *reinterpret_cast<const f32x2*>(prm + KS * KS * 128 + hl * 8);
+                    const f32x2 bi2 = *reinterpret_cast<const f32x2*>(prm + KS * KS * 128 + 256 + hl * 8);
+                    f32x2 acc[2][4];
+#pragma unroll
+                    for (int a = 0; a < 2; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) acc[a][b] = 0ull;
+                    f32x2 wq[KS][KS];
+#pragma unroll
+                    for (int iy = 0; iy < 1 + KS; ++iy) {           // 2 output rows need 2 - 1 + KS input rows
+                        if (iy < KS) {
+#pragma unroll
+                            for (int kx = 0; kx < KS; ++kx)
+                                wq[iy][kx] = MF::widen(*reinterpret_cast<const uint32_t*>(prm + (iy * KS + kx) * 128 + hl * 4));
+                        }
+                        f32x2 row[IBW];
+#pragma unroll
+                        for (int ix = 0; ix < IBW; ++ix) row[ix] = MF::widen(*reinterpret_cast<const uint32_t*>(in_h + (iy * IW + ix) * 128));
+#pragma unroll
+                        for (int oy = 0; oy < 2; ++oy) {
+                            const int ky = iy - oy;
+                            if (ky < 0 || ky >= KS) continue;
+#pragma unroll
+                            for (int ox = 0; ox < 4; ++ox)
+#pragma unroll
+                                for (int kx = 0; kx < KS; ++kx) ffma2(acc[oy][ox], row[ox + kx], wq[ky][kx]);
+                            if (ky == KS - 1) {
+#pragma unroll
+                                for (int ox = 0; ox < 4; ++ox) {
+                                    const int m = (ni * TH + br * 4 + hh * 2 + oy) * TW + bc * 4 + ox;
+                                    *reinterpret_cast<uint32_t*>(a_s + m * 128 + (((hl >> 2) ^ (m & 7)) << 4) + ((hl & 3) << 2)) =
+                                        MF::template pack_act<RELU6>(ffma2_abc(acc[oy][ox], sc2, bi2));
+                                }
+                            }
+                        }
+                    }
+                } else if constexpr (kDwFfma2) {
                     // Inner product on FFMA2: every 16-bit word (the lane's channel pair) is widened to an fp32 pair once
                     // (two HADD2.F32), then ONE two-wide FMA per pixel-tap instead of two FHFMA: 144 FFMA2 + 90 HADD2 against
                     // 288 FHFMA per 4x4 block.  Bit-identical (a 16-bit x 16-bit product is exact in either FMA); FFMA2 issues
@@ -542,9 +595,12 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                     }
                 }
             } else {
-                // decode_conv6 folded below the last upsample: dot over this block's (<= 64) output channels
+                // decode_conv6 folded below the last upsample: dot over this block's (<= 64) output channels, on channel PAIRS:
+                // BN affine as one FFMA2, ReLU folded into the 16-bit rounding (decode_conv5's output IS stored in 16 bits in the
+                // reference), then the head's 16-bit weights times the 16-bit activations on the mixed-precision FMA (exact
+                // products, fp32 accumulation) -- 6 instructions per pair instead of 11
                 const int batches = (p.n_cta + 31) >> 5;
-                float dot = 0.f;
+                float dot_lo = 0.f, dot_hi = 0.f;
                 for (int b = 0; b < batches; ++b) {
                     uint32_t r[32];
                     const bool full = b * 32 + 32 <= p.n_cta;
@@ -555,14 +611,12 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                         if (j >= 8 && !full) break;
                         const int c0 = b * 32 + 2 * j;
                         const float4 af = *reinterpret_cast<const float4*>(s_pw_affine + c0);
-                        const float2 hw = *reinterpret_cast<const float2*>(s_head_w + c0);
-                        const float lo = affine_act<RELU6>(__uint_as_float(r[2 * j]), af.x, af.z);
-                        const float hi = affine_act<RELU6>(__uint_as_float(r[2 * j + 1]), af.y, af.w);
-                        const float2 rq = MF::unpack(MF::pack(lo, hi));      // decode_conv5's output is stored in 16 bits
-                        dot = fmaf(rq.x, hw.x, dot);
-                        dot = fmaf(rq.y, hw.y, dot);
+                        const uint32_t h = MF::template pack_act<RELU6>(ffma2_abc(
+                            f32x2_make(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), f32x2_make(af.x, af.y), f32x2_make(af.z, af.w)));
+                        MF::fma2(dot_lo, dot_hi, h, s_head_w2[c0 >> 1]);
                     }
                 }
+                const float dot = dot_lo + dot_hi;
                 tc_fence_before();                                       // accumulator drained
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));
@@ -593,9 +647,6 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
 // ----------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------
-int g_use_pdl = 1;
-int g_wait_sleep_ns = 0;
-
 PFN_encodeTiled get_tensor_map_encoder() {
     static PFN_encodeTiled fn = nullptr;
     if (fn) return fn;
@@ -613,6 +664,8 @@ struct BlockTcPlan {
     dim3 grid;
     size_t smem_bytes;
     int dtype, ks, stride, tile;           // tile: 0 = (1,8,16), 1 = (2,8,8)
+    int halfk = 0;                         // 1: c_in <= 32, the HALFK instance of the 3x3 stride-1 kernel
+    TcLaunchOpts opts;                     // the plan's launch options at the time this block was prepared
     void* dwp = nullptr;                   // owned device copies (packed / padded)
     float2* pw_affine = nullptr;
     float* head_w = nullptr;
@@ -642,35 +695,37 @@ bool block_tc_supported(int dtype, const StageGeom& g, bool head_fused) {
     return get_encode() != nullptr;
 }
 
-template <typename T, int KS, int STRIDE, int NI, int TH, int TW, bool RELU6>
+template <typename T, int KS, int STRIDE, int NI, int TH, int TW, bool RELU6, bool HALFK = false>
 static int launch_inst2(BlockTcPlan* bp, cudaStream_t st) {
-    auto kern = block_tc_kernel<T, KS, STRIDE, NI, TH, TW, RELU6>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    auto kern = block_tc_kernel<T, KS, STRIDE, NI, TH, TW, RELU6, HALFK>;
+    static PerDeviceOnce attr_set;             // the opt-in is per device (and per kernel instance)
+    int dev = -1;
+    FD_CUDA_OK(cudaGetDevice(&dev));
+    if (attr_set.need(dev)) {
         FD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
+        attr_set.done(dev);
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = bp->grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = bp->smem_bytes; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
-    bp->p.sleep_ns = g_wait_sleep_ns;
+    cfg.attrs = attr; cfg.numAttrs = bp->opts.pdl ? 1 : 0;
     FD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, bp->tm_in, bp->tm_w, bp->tm_o[0], bp->tm_o[1], bp->tm_o[2], bp->tm_o[3], bp->p));
     FD_CUDA_OK(cudaGetLastError());
     return FD_OK;
 }
-template <typename T, int KS, int STRIDE, int NI, int TH, int TW>
+template <typename T, int KS, int STRIDE, int NI, int TH, int TW, bool HALFK = false>
 static int launch_inst(BlockTcPlan* bp, cudaStream_t st) {
-    return bp->p.act == FD_ACT_RELU6 ? launch_inst2<T, KS, STRIDE, NI, TH, TW, true>(bp, st)
-                                     : launch_inst2<T, KS, STRIDE, NI, TH, TW, false>(bp, st);
+    return bp->p.act == FD_ACT_RELU6 ? launch_inst2<T, KS, STRIDE, NI, TH, TW, true, HALFK>(bp, st)
+                                     : launch_inst2<T, KS, STRIDE, NI, TH, TW, false, HALFK>(bp, st);
 }
 
 template <typename T>
 static int launch_t(BlockTcPlan* bp, cudaStream_t st) {
-    const int key = bp->ks * 100 + bp->stride * 10 + bp->tile;
+    const int key = bp->halfk * 1000 + bp->ks * 100 + bp->stride * 10 + bp->tile;
     switch (key) {
+        case 1310: return launch_inst<T, 3, 1, 1, 8, 16, true>(bp, st);
         case 310: return launch_inst<T, 3, 1, 1, 8, 16>(bp, st);
         case 311: return launch_inst<T, 3, 1, 2, 8, 8>(bp, st);
         case 320: return launch_inst<T, 3, 2, 1, 8, 16>(bp, st);
@@ -698,7 +753,7 @@ BlockPlanOut block_tc_debug_plan(int ksize, int stride, int h_out, int w_out, in
     q.ksize = ksize; q.stride = stride; q.tile = pick_tile(g); q.c_in = c_in; q.c_out = c_out; q.head = head;
     const int NI = q.tile ? 2 : 1, TW = q.tile ? 8 : 16;
     q.n_tiles = ((w_out + TW - 1) / TW) * ((h_out + 7) / 8) * ((n + NI - 1) / NI);
-    q.barrier_bytes = (int)sizeof(TcBarriers);
+    q.barrier_bytes = (int)sizeof(TcBarriers); q.n_sms = 148;
     plan_env_knobs(q);
     return plan_block(q);
 }
@@ -762,13 +817,18 @@ static int padded_copy(const float* src, int n_src, int n_dst, float** out) {
 }
 
 int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float head_scale, float head_bias, int head_act,
-                     void* head_out, bool tma_epilogue, BlockTcPlan** out) {
+                     void* head_out, bool tma_epilogue, const TcLaunchOpts& opts, BlockTcPlan** out) {
     PFN_encodeTiled encode = get_encode();
     if (!encode) return fail(FD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     const StageGeom& g = a.g;
     BlockTcPlan* bp = new (std::nothrow) BlockTcPlan();
     if (!bp) return fail(FD_ERR_CUDA, "out of host memory");
     bp->dtype = dtype; bp->ks = g.ksize; bp->stride = g.stride; bp->tile = pick_tile(g);
+    bp->opts = opts;
+    {
+        const char* e = getenv("FD_TC_NO_HALFK");            // experiment knob
+        bp->halfk = (g.c_in <= 32 && g.ksize == 3 && g.stride == 1 && bp->tile == 0 && !(e && *e == '1')) ? 1 : 0;
+    }
     const int NI = bp->tile ? 2 : 1, TH = 8, TW = bp->tile ? 8 : 16;
     const int IH = (TH - 1) * g.stride + g.ksize, IW = (TW - 1) * g.stride + g.ksize;
     TcParams& p = bp->p;
@@ -786,7 +846,7 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
 
     BlockPlanIn pin{};
     pin.ksize = g.ksize; pin.stride = g.stride; pin.tile = bp->tile; pin.c_in = g.c_in; pin.c_out = g.c_out; pin.n_tiles = n_tiles;
-    pin.head = p.head; pin.barrier_bytes = (int)sizeof(TcBarriers);
+    pin.head = p.head; pin.barrier_bytes = (int)sizeof(TcBarriers); pin.n_sms = opts.n_sms;
     plan_env_knobs(pin);
     const BlockPlanOut po = plan_block(pin);
     if (!po.ok) { delete bp; return fail(FD_ERR_UNSUPPORTED, "fused block does not fit shared memory"); }
@@ -799,8 +859,13 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
     bp->smem_bytes = (size_t)po.smem_bytes;
     const int taps = g.ksize * g.ksize;
     (void)splits;
-    int sms = 148;
-    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int sms = opts.n_sms;
+    p.sleep_ns = opts.sleep_ns;
+    {   // experiment knobs (environment, read when a plan is built)
+        const char* a = getenv("FD_TC_MMA_SLEEP"); const char* b = getenv("FD_TC_DW_SLEEP");
+        p.mma_sleep_ns = a ? atoi(a) : 0;
+        p.dw_sleep_ns = b ? atoi(b) : 0;
+    }
     bp->grid = dim3((unsigned)(p.items < sms ? p.items : sms), 1, 1);
 
     // packed / padded parameter copies (device -> device)
@@ -866,7 +931,7 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
         }
     }
     char buf[160];
-    snprintf(buf, sizeof(buf), "block_tc<k%d,s%d,%s>%s%s%s[n%dx%d,bn%d%s,kb%d,in%d,a%d,b%d,e%dx%d%s]", g.ksize, g.stride, bp->tile ? "2x8x8" : "1x8x16",
+    snprintf(buf, sizeof(buf), "block_tc<k%d,s%d,%s%s>%s%s%s[n%dx%d,bn%d%s,kb%d,in%d,a%d,b%d,e%dx%d%s]", g.ksize, g.stride, bp->tile ? "2x8x8" : "1x8x16", bp->halfk ? ",k32" : "",
              g.upsample ? "+up2x" : "", a.skip ? (p.epi_red ? "+skip(red)" : "+skip") : "", p.head ? "+head" : (p.epi_tma ? "+tmast" : ""), p.n_cta, p.splits, p.bn,
              p.b_resident ? "r" : "", p.kblocks, p.s_in, p.s_a, p.s_b, p.epi_groups, p.head ? 0 : p.n_stg / p.epi_groups, p.epi_colsplit ? "c" : (p.epi_wide ? "w" : ""));
     bp->name = buf;

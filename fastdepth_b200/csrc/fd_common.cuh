@@ -119,6 +119,21 @@ struct StageGeom {
     int skip_pitch;                    // same for the skip tensor of an ADD stage
 };
 
+// Launch-time options of a plan (fd_plan_set_option), copied into every kernel plan when it is built so that two plans with
+// different options never share mutable state.
+struct TcLaunchOpts {
+    int pdl = 1;             // programmatic dependent launch attribute on every launch
+    int sleep_ns = 0;        // > 0: latency-tolerant mbarrier waits back off with nanosleep instead of spinning
+    int n_sms = 148;         // SMs of the plan's device (grid size and the planner's wave model)
+};
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE property of a kernel: remember which devices have it.
+struct PerDeviceOnce {
+    unsigned long long mask = 0;
+    bool need(int dev) const { return dev < 0 || dev >= 64 || !((mask >> dev) & 1ull); }
+    void done(int dev) { if (dev >= 0 && dev < 64) mask |= 1ull << dev; }
+};
+
 // Launch argument bundle for one fused / unfused block stage.
 struct BlockArgs {
     StageGeom g;

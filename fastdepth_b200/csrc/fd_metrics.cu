@@ -4,8 +4,9 @@
 // time, which is what its only caller does (DataLoader batch_size=1, main.py:40-41, 80-82), and
 // AverageMeter's running sums (metrics.py:71-95): for every image the 10 metric values are added
 // to sums[0..9] and 1 to sums[10].  The caller divides by the count after its single cross-GPU
-// all-reduce.  Element math is fp32 like the reference; the reductions
-// use double accumulators (the reference's fp32 cascade sum agrees to ~1e-6 relative).
+// all-reduce.  Element math is fp32 like the reference; the per-image reductions
+// use double accumulators (the reference's fp32 cascade sum agrees to ~1e-6 relative) and the per-image
+// results are rounded to fp32, the precision the reference carries them in.
 #include "fd_common.cuh"
 
 namespace fd {
@@ -64,7 +65,11 @@ metrics_kernel(const T* __restrict__ pred, const float* __restrict__ target, int
         const double mse = tot[1] / cnt;
         const double vals[10] = {sqrt(tot[8] / cnt), tot[9] / cnt, mse,          sqrt(mse),     tot[2] / cnt,
                                  tot[4] / cnt,       tot[3] / cnt, tot[5] / cnt, tot[6] / cnt, tot[7] / cnt};
-        for (int i = 0; i < 10; ++i) atomicAdd(&sums[i], vals[i]);
+        // The reference's per-image values are fp32 (float(tensor.mean()), metrics.py:38-55) and AverageMeter adds them up in
+        // double: round every per-image value to fp32 before the fp64 accumulation.  A sum of 24-bit values of similar
+        // magnitude is then EXACT in fp64, i.e. independent of the order of the atomics and of how images are partitioned
+        // over ranks -- the N-rank sums equal the 1-rank sums bit for bit.
+        for (int i = 0; i < 10; ++i) atomicAdd(&sums[i], (double)(float)vals[i]);
         atomicAdd(&sums[10], 1.0);
     }
 }

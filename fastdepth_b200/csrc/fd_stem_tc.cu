@@ -218,6 +218,7 @@ struct StemTcPlan {
     dim3 grid;
     size_t smem_bytes;
     int dtype;
+    TcLaunchOpts opts;
     const void* x_bound = nullptr;       // input pointer the tensor map was encoded for
     void* w16 = nullptr;                 // [n_pad][64] 16-bit, K = (ci, ky, kx) padded
     float2* affine = nullptr;
@@ -271,7 +272,7 @@ static int encode_input_map(StemTcPlan* sp, const void* x) {
 }
 
 int stem_tc_prepare(int dtype, const StageGeom& g, const float* w27_dev, const float* scale_dev, const float* bias_dev, void* out,
-                    StemTcPlan** res) {
+                    const TcLaunchOpts& opts, StemTcPlan** res) {
     PFN_encodeTiled encode = get_tensor_map_encoder();
     if (!encode) return fail(FD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     StemTcPlan* sp = new (std::nothrow) StemTcPlan();
@@ -313,8 +314,8 @@ int stem_tc_prepare(int dtype, const StageGeom& g, const float* w27_dev, const f
     }
     sp->smem_bytes = (size_t)ST_S_A * ST_A_BYTES + (size_t)p.n_pad * 128 + (size_t)ST_S_IN * ST_IN_STRIDE + (size_t)p.n_pad * 8 +
                      sizeof(StemBarriers) + 1024;
-    int sms = 148;
-    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int sms = opts.n_sms;
+    sp->opts = opts;
     sp->grid = dim3((unsigned)(p.items < sms ? p.items : sms), 1, 1);
     char buf[96];
     snprintf(buf, sizeof(buf), "stem_tc<k3,s2,1x8x16>[n%d]", p.n_pad);
@@ -338,13 +339,15 @@ int stem_tc_launch(StemTcPlan* sp, const void* x, cudaStream_t st) {
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
-    static bool attr_done[2] = {false, false};
+    cfg.attrs = attr; cfg.numAttrs = sp->opts.pdl ? 1 : 0;
+    static PerDeviceOnce attr_done[2];         // the dynamic shared-memory opt-in is per device and per kernel instance
+    int dev = -1;
+    FD_CUDA_OK(cudaGetDevice(&dev));
     if (sp->dtype == FD_F16) {
-        if (!attr_done[0]) { FD_CUDA_OK(cudaFuncSetAttribute(stem_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done[0] = true; }
+        if (attr_done[0].need(dev)) { FD_CUDA_OK(cudaFuncSetAttribute(stem_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done[0].done(dev); }
         FD_CUDA_OK(cudaLaunchKernelEx(&cfg, stem_tc_kernel<__half>, sp->tm_in, sp->tm_w, sp->p));
     } else {
-        if (!attr_done[1]) { FD_CUDA_OK(cudaFuncSetAttribute(stem_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done[1] = true; }
+        if (attr_done[1].need(dev)) { FD_CUDA_OK(cudaFuncSetAttribute(stem_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_done[1].done(dev); }
         FD_CUDA_OK(cudaLaunchKernelEx(&cfg, stem_tc_kernel<__nv_bfloat16>, sp->tm_in, sp->tm_w, sp->p));
     }
     FD_CUDA_OK(cudaGetLastError());

@@ -260,7 +260,6 @@ __device__ __forceinline__ float affine_act(float acc, float s, float b) {
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-PFN_encodeTiled get_tensor_map_encoder();
-extern int g_use_pdl;                          // set from fd_plan option "pdl" before launching     // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (no libcuda link)
+PFN_encodeTiled get_tensor_map_encoder();       // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (no libcuda link)
 
 }  // namespace fd

@@ -20,13 +20,17 @@ class SkipAddEngine:
 
     # -- weight freshness ----------------------------------------------------------------------
     def _weights_signature(self):
-        """Cheap per-call check that catches .cuda()/.half()/.to()/load_state_dict().
-        In-place edits of a single layer need an explicit ``refresh()``."""
-        enc, _, head, _, _ = _plan._blocks_of(self.module)
-        w0 = enc[0][0].weight
-        bn = head[1]
-        return (w0.data_ptr(), w0.dtype, w0._version, bn.running_var.data_ptr(), bn.running_var._version,
-                bn.weight._version)
+        """Per-call freshness check over EVERY parameter and buffer of the module: storage pointer, dtype and the
+        autograd version counter (bumped by every in-place write through the tensor itself: ``load_state_dict``,
+        ``p.copy_`` / ``p.mul_`` under ``no_grad``, optimizer steps).  ~250 tensors, a few tens of microseconds; catches
+        .cuda()/.half()/.to() too.  Writes that bypass the counter (``p.data.mul_()``, a raw pointer handed to another
+        library) still need an explicit ``refresh()``."""
+        sig = []
+        for t in self.module.parameters():
+            sig.append((t.data_ptr(), t.dtype, t._version))
+        for t in self.module.buffers():
+            sig.append((t.data_ptr(), t.dtype, t._version))
+        return tuple(sig)
 
     def refresh(self):
         """Drop packed weights (call after editing parameters in place)."""

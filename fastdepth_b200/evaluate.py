@@ -41,9 +41,10 @@ def finalize(sums):
 
 
 @torch.no_grad()
-def evaluate(model, batches, device, group=None):
+def evaluate(model, batches, device, group=None, return_sums=False):
     """``batches`` yields (input [b,3,H,W], target [b,1,H,W]) for THIS rank's shard (host or
-    device tensors).  Returns the averaged metrics over all ranks' images."""
+    device tensors).  Returns the averaged metrics over all ranks' images (with ``return_sums`` also the reduced
+    11-double sum vector, for bookkeeping checks)."""
     sums = new_sums(device)
     model.eval()
     dtype = next(model.parameters()).dtype
@@ -53,4 +54,4 @@ def evaluate(model, batches, device, group=None):
         pred = model(inp)
         metrics_accumulate(pred, tgt, sums)
     reduce_sums(sums, group)
-    return finalize(sums)
+    return (finalize(sums), sums) if return_sums else finalize(sums)

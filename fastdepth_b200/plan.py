@@ -114,6 +114,8 @@ def describe(module):
     for j in range(1, 6):
         blk = dec[j - 1]
         (dw, bn1, a1), (pw, bn2, a2) = (blk[0][0], blk[0][1], blk[0][2]), (blk[1][0], blk[1][1], blk[1][2])
+        if _act_of(a1) != _act_of(a2):
+            raise RuntimeError('decoder block %d: mixed activations are not supported' % j)
         skip = stage_of_encoder[SKIP_FOR_DECODE[j]] if (with_skips and j in SKIP_FOR_DECODE) else -1
         descs.append(dict(kind=_lib.FD_STAGE_DWPW, c_in=dw.weight.shape[0], c_out=pw.weight.shape[0],
                           ksize=_sq(dw.kernel_size), stride=1, act=_act_of(a1), upsample=1, skip_src=skip,
@@ -204,8 +206,10 @@ class Plan:
             buf = ctypes.create_string_buffer(96)
             _lib.check(self.lib.fd_plan_step_info(self.handle, i, ctypes.byref(st), ctypes.byref(ab), ctypes.byref(mc),
                                                   buf, 96))
+            dwm, dnm = ctypes.c_double(), ctypes.c_double()
+            _lib.check(self.lib.fd_plan_step_macs(self.handle, i, ctypes.byref(dwm), ctypes.byref(dnm)))
             out.append(dict(step=i, stage=st.value, stage_name=self.names[st.value], kernel=buf.value.decode(),
-                            alg_bytes=ab.value, macs=mc.value))
+                            alg_bytes=ab.value, macs=mc.value, dw_macs=dwm.value, dense_macs=dnm.value))
         return out
 
     def time_steps(self, x, y, stream_ptr, warmup=3, iters=20, flush_l2=True):

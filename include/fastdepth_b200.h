@@ -146,6 +146,10 @@ int fd_plan_step_count(fd_plan* plan, int* n_steps);
  * section 8d) and MACs of step `step`, plus its kernel name. */
 int fd_plan_step_info(fd_plan* plan, int step, int* stage, double* alg_bytes, double* macs,
                       char* kernel_name, int name_cap);
+/* The same step's MACs split by the pipe that executes them: depthwise taps (channel-wise, SIMT FMA pipe; north_star keeps
+ * them off the tensor cores) and the dense contractions (stem im2col, pointwise 1x1, head; tensor pipe on path 1).  bench.py
+ * turns them into the per-stage FMA-pipe and tensor-pipe floors it prints next to the HBM floor. */
+int fd_plan_step_macs(fd_plan* plan, int step, double* dw_macs, double* dense_macs);
 /* Time every step's kernel alone with CUDA events on `stream` (`warmup` + `iters` launches each;
  * a 256 MB buffer is written between launches when flush_l2 != 0 so inputs come from HBM).
  * ms_out[n_steps] = mean launch duration.  Synchronous. */

@@ -173,7 +173,9 @@ class MobileNet(nn.Module):
         """CPU tensors (BASELINE config 1 plumbing) and the dense 5x5 decoder run on stock PyTorch, exactly like the
         reference (models.py:457-460).  A CUDA tensor through the depthwise NNConv decoder ("MobileNet-NNConv5(dw)",
         reference README.md:37) takes the same fused sm_100a path as MobileNetSkipAdd, just without skips."""
-        if x.is_cuda and not self.training:
+        fused_ok = (x.is_cuda and not self.training and x.dim() == 4 and x.shape[1] == 3 and
+                    x.shape[2] % 32 == 0 and x.shape[3] % 32 == 0)     # what the fused plan covers; anything else: stock PyTorch
+        if fused_ok:
             from fastdepth_b200 import plan as _plan
             if _plan.supports(self):
                 engine = self.__dict__.get('_fd_engine')
