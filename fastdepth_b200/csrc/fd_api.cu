@@ -40,6 +40,13 @@ int block_tc_launch(BlockTcPlan* p, cudaStream_t st, void* head_out);
 void block_tc_destroy(BlockTcPlan* p);
 const char* block_tc_name(BlockTcPlan* p);
 int block_tc_trace(BlockTcPlan* bp, cudaStream_t st, void* head_out, unsigned long long* out_host, int* rows, int* cols);
+// fused multi-layer chain kernel (fd_chain_tc.cu): a run of 3x3 stride-1 blocks on a small map in one 2-CTA-cluster kernel
+struct ChainTcPlan;
+bool chain_tc_supported(int dtype, const StageGeom* g, int n_layers);
+int chain_tc_prepare(int dtype, const BlockArgs* layers, int n_layers, const TcLaunchOpts& opts, ChainTcPlan** out);
+int chain_tc_launch(ChainTcPlan* cp, cudaStream_t st);
+void chain_tc_destroy(ChainTcPlan* cp);
+const char* chain_tc_name(ChainTcPlan* cp);
 // tensor-core stem (fd_stem_tc.cu)
 struct StemTcPlan;
 bool stem_tc_supported(int dtype, const StageGeom& g);
@@ -73,6 +80,9 @@ struct Stage {
     bool have_weights = false;
     BlockTcPlan* tc = nullptr;
     StemTcPlan* stc = nullptr;
+    ChainTcPlan* chain = nullptr;        // set on the FIRST stage of a run executed by the chain kernel
+    int chained = 0;                     // 1: this stage runs inside a chain kernel (its own output buffer is only written if it is
+                                         //    the run's last stage)
 };
 
 struct Step {
@@ -93,6 +103,7 @@ struct fd_plan {
     std::vector<Step> steps;
     bool steps_valid = false;
     int opt_path = 1, opt_fold_head = 1, opt_graph = 1, opt_tma_epilogue = 1, opt_inplace_skip = 1, opt_pdl = 1, opt_wait_sleep_ns = 0;
+    int opt_chain = 1;
     size_t workspace_bytes = 0;
     // fd_pipeline_*: host batches flow H2D -> forward -> D2H through kPipeSlots device slots on three streams
     struct PipeSlot { void* x = nullptr; void* y = nullptr; cudaEvent_t up = nullptr, done = nullptr, down = nullptr; bool busy = false; };
@@ -142,6 +153,8 @@ static void invalidate(fd_plan* p) {
     for (auto& s : p->stages) {
         if (s.tc) { block_tc_destroy(s.tc); s.tc = nullptr; }
         if (s.stc) { stem_tc_destroy(s.stc); s.stc = nullptr; }
+        if (s.chain) { chain_tc_destroy(s.chain); s.chain = nullptr; }
+        s.chained = 0;
     }
 }
 
@@ -205,7 +218,62 @@ static int build_steps(fd_plan* p) {
                 };
             }
             p->steps.push_back(st);
+        } else if (s.d.kind == FD_STAGE_DWPW && s.chained) {
+            continue;                                 // executed by the chain kernel launched at the run's first stage
         } else if (s.d.kind == FD_STAGE_DWPW) {
+            // ---- a run of 3x3 stride-1 blocks on a small map: ONE chain kernel (2-CTA clusters, activations stay in shared memory)
+            if (p->opt_path == 1 && p->opt_chain) {
+                std::vector<BlockArgs> run;
+                std::vector<StageGeom> geoms;
+                int j = i;
+                for (; j < ns - 1 && (int)run.size() < 8; ++j) {
+                    Stage& t = p->stages[j];
+                    if (t.d.kind != FD_STAGE_DWPW || t.d.ksize != 3 || t.d.stride != 1 || t.d.upsample || t.d.skip_src >= 0) break;
+                    if (j > i && p->stages[j - 1].concat_src >= 0) break;     // the previous output must really be written (concat slice)
+                    bool is_skip_source = false;                              // ... and so must a tensor a decoder stage will add / concatenate
+                    for (int k2 = j + 1; k2 < ns; ++k2) if (p->stages[k2].d.skip_src == j) is_skip_source = true;
+                    BlockArgs b{};
+                    b.g = t.g;
+                    b.g.in_pitch = j > 0 ? p->stages[j - 1].out_pitch : 0;
+                    b.g.out_pitch = t.out_pitch;
+                    b.in = j > 0 ? p->stages[j - 1].out_eff : nullptr;
+                    b.out = t.out;
+                    b.dw_w = t.dw_w; b.dw_scale = t.dw_scale; b.dw_bias = t.dw_bias;
+                    b.pw_w = t.pw_w; b.pw_scale = t.pw_scale; b.pw_bias = t.pw_bias;
+                    run.push_back(b); geoms.push_back(b.g);
+                    if (is_skip_source) { ++j; break; }                       // a skip source may END a run, not sit inside one
+                }
+                int len = (int)run.size();
+                while (len >= 2 && !chain_tc_supported(p->dtype, geoms.data(), len)) --len;
+                if (len >= 2) {
+                    int rc = chain_tc_prepare(p->dtype, run.data(), len, lopts, &s.chain);
+                    if (rc != FD_OK) return rc;
+                    Step st;
+                    st.stage = i + len - 1;                                   // reported under the run's last stage (the tensor it writes)
+                    st.macs = 0; st.dw_macs = 0;
+                    double wb = 0;
+                    for (int k2 = 0; k2 < len; ++k2) {
+                        const StageGeom& g = geoms[k2];
+                        const double px = (double)g.n * g.h_out * g.w_out;
+                        st.dw_macs += px * g.c_in * 9.0;
+                        st.macs += px * g.c_in * 9.0 + px * g.c_in * g.c_out;
+                        wb += (double)g.c_in * 9 * 4 + 2.0 * g.c_in * 4 + (double)g.c_in * g.c_out * es + 2.0 * g.c_out * 4;
+                        p->stages[i + k2].chained = 1;
+                        p->stages[i + k2].out_eff = p->stages[i + k2].out;
+                    }
+                    // algorithmic bytes of the MERGED stage (SURVEY.md 8d rule): external input once + external output once + weights once
+                    st.alg_bytes = ((double)geoms[0].n * geoms[0].h_in * geoms[0].w_in * geoms[0].c_in +
+                                    (double)geoms[len - 1].n * geoms[len - 1].h_out * geoms[len - 1].w_out * geoms[len - 1].c_out) * es + wb;
+                    char nm[200];
+                    snprintf(nm, sizeof(nm), "%s{stages %d-%d}", chain_tc_name(s.chain), i, i + len - 1);
+                    st.name = nm;
+                    ChainTcPlan* cpn = s.chain;
+                    st.run = [cpn](cudaStream_t stream, const void*, void*) { return chain_tc_launch(cpn, stream); };
+                    p->steps.push_back(st);
+                    s.chained = 1;
+                    continue;
+                }
+            }
             BlockArgs a{};
             a.g = s.g;
             const bool folded_here = fold && (&s == &last);
@@ -449,6 +517,7 @@ static int* option_slot(fd_plan* p, const char* name) {
     if (!strcmp(name, "inplace_skip")) return &p->opt_inplace_skip;
     if (!strcmp(name, "pdl")) return &p->opt_pdl;
     if (!strcmp(name, "wait_sleep_ns")) return &p->opt_wait_sleep_ns;
+    if (!strcmp(name, "chain")) return &p->opt_chain;
     return nullptr;
 }
 

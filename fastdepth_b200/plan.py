@@ -203,12 +203,17 @@ class Plan:
         out = []
         for i in range(n.value):
             st, ab, mc = ctypes.c_int(), ctypes.c_double(), ctypes.c_double()
-            buf = ctypes.create_string_buffer(96)
+            buf = ctypes.create_string_buffer(200)
             _lib.check(self.lib.fd_plan_step_info(self.handle, i, ctypes.byref(st), ctypes.byref(ab), ctypes.byref(mc),
-                                                  buf, 96))
+                                                  buf, 200))
             dwm, dnm = ctypes.c_double(), ctypes.c_double()
             _lib.check(self.lib.fd_plan_step_macs(self.handle, i, ctypes.byref(dwm), ctypes.byref(dnm)))
-            out.append(dict(step=i, stage=st.value, stage_name=self.names[st.value], kernel=buf.value.decode(),
+            kname = buf.value.decode()
+            sname = self.names[st.value]
+            if 'chain_tc' in kname and '{stages ' in kname:            # one kernel for a run of stages: name the run
+                a, b = kname.split('{stages ')[1].rstrip('}').split('-')
+                sname = '%s..%s' % (self.names[int(a)], self.names[int(b)])
+            out.append(dict(step=i, stage=st.value, stage_name=sname, kernel=kname,
                             alg_bytes=ab.value, macs=mc.value, dw_macs=dwm.value, dense_macs=dnm.value))
         return out
 

@@ -106,6 +106,9 @@ int fd_plan_set_stage_weights(fd_plan* plan, int stage,
  *                after fd_forward (set 0 for stage-by-stage inspection)  [default 1]
  *   "pdl"        1 = tensor-core kernels are launched with programmatic dependent launch so that each
  *                kernel's prologue overlaps the previous kernel's tail  [default 1]
+ *   "chain"      1 = a run of consecutive 3x3 stride-1 blocks on a small feature map (conv7..conv11 at 14x14) executes as ONE
+ *                kernel on 2-CTA clusters with every intermediate activation resident in shared memory; the intermediate
+ *                stages' buffers are then not written (set 0 for stage-by-stage inspection)  [default 1]
  *   "wait_sleep_ns" > 0: latency-tolerant roles of the fused block kernel (epilogue warps waiting for an
  *                accumulator, TMA producer waiting for a free stage) sleep this many ns between barrier
  *                probes instead of spinning (measured: no effect on B200, the spinning waiters do not
