@@ -56,5 +56,24 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(tag, defines):
+    """Developer A/B: a second library with extra -D flags (e.g. FD_TC_EPI_FIRST), loaded through FD_B200_LIB."""
+    lib = os.path.join(HERE, 'libfastdepth_b200_%s.so' % tag)
+    objs = []
+    for s in SOURCES:
+        src = os.path.join(CSRC, s)
+        o = os.path.join(CSRC, s[:-3] + '.%s.o' % tag)
+        objs.append(o)
+        cmd = [_nvcc()] + NVCC_FLAGS + ['-D' + d for d in defines] + ['-c', src, '-o', o]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('nvcc failed: %s\n%s' % (' '.join(cmd), r.stdout))
+    r = subprocess.run([_nvcc(), '-shared', '-o', lib] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a'],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('link failed\n' + r.stdout)
+    return lib
+
+
 if __name__ == '__main__':
     print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

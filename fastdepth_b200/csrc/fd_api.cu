@@ -47,6 +47,7 @@ int chain_tc_prepare(int dtype, const BlockArgs* layers, int n_layers, const TcL
 int chain_tc_launch(ChainTcPlan* cp, cudaStream_t st);
 void chain_tc_destroy(ChainTcPlan* cp);
 const char* chain_tc_name(ChainTcPlan* cp);
+int chain_tc_trace(ChainTcPlan* cp, cudaStream_t st, unsigned long long* out_host, int* rows, int* cols);
 // tensor-core stem (fd_stem_tc.cu)
 struct StemTcPlan;
 bool stem_tc_supported(int dtype, const StageGeom& g);
@@ -780,8 +781,9 @@ int fd_plan_trace_stage(fd_plan* p, int stage, void* y_dev, void* stream, unsign
     DeviceGuard guard(p->device);
     int rc = ensure_steps(p);
     if (rc) return rc;
-    if (!p->stages[stage].tc) return fail(FD_ERR_STATE, "stage does not run the fused block kernel");
     if (cap < 12 * 256) return fail(FD_ERR_INVALID, "trace buffer too small (need 3072 entries)");
+    if (p->stages[stage].chain) return chain_tc_trace(p->stages[stage].chain, (cudaStream_t)stream, out_host, rows, cols);
+    if (!p->stages[stage].tc) return fail(FD_ERR_STATE, "stage does not run the fused block kernel");
     return block_tc_trace(p->stages[stage].tc, (cudaStream_t)stream, y_dev, out_host, rows, cols);
 }
 

@@ -81,6 +81,7 @@ struct ChainParams {
     int n_zero[2];
     void* out;
     ChainLayer L[CH_MAX_LAYERS];
+    unsigned long long* trace;         // debug timeline (fd_plan_trace_stage) or nullptr: [12 rows][256] SM clocks of the leader CTA of cluster 0
     unsigned char zero_slots[2][48];   // per cluster rank: pixel slots that must read as zero for the next layer (padding column,
                                        // image-border halo row); re-zeroed after every layer because the in-place operand tile
                                        // has overwritten slots 0..127
@@ -137,6 +138,11 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {      // arrive o
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
+#define CH_TRACE(row, idx)                                                                                \
+    do {                                                                                                  \
+        if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 256) p.trace[(row) * 256 + (idx)] = clock64(); \
+    } while (0)
+
 // ----------------------------------------------------------------------------------------------------------
 template <typename T, bool RELU6>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1)
@@ -189,6 +195,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                         for (int nh = 0; nh < L.nh; ++nh, ++seq) {
                             const uint32_t s = seq & (CH_SB - 1), ph = (seq / CH_SB) & 1u;
                             mbar_wait_sleep(smem_u32(&bars->b_empty[s]), ph ^ 1u, (uint32_t)p.sleep_ns);
+                            if (kb == 0 && nh == 0 && img == cluster_id) CH_TRACE(10, l);
                             const int n_ins = min(256, L.n_pad - nh * 256);
                             if (rank == 0) mbar_expect_tx(smem_u32(&bars->b_full[s]), 2u * CH_B_STAGE);
                             tma_load_2d_2sm(smem_base + CH_OFF_B + s * CH_B_STAGE, &maps.w[l], leader_b_full0 + 8u * s, kb * 64,
@@ -220,9 +227,10 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
             uint32_t it = 0, acc_seq = 0;
             for (int img = cluster_id; img < p.n_img; img += n_clusters, ++it) {
                 if (it > 0) {
-                    // the activation blocks are free once the previous image's last layer has finished its MMAs
-                    acc_seq += (uint32_t)p.n_layers;
-                    mbar_wait_sleep(smem_u32(&bars->acc_full), (acc_seq - 1u) & 1u, (uint32_t)p.sleep_ns);
+                    // the activation blocks are free once the previous image's LAST layer has finished its MMAs: follow the
+                    // accumulator barrier through every layer's phase (a parity alone cannot tell phase 0 from phase 4)
+                    for (int l = 0; l < p.n_layers; ++l, ++acc_seq)
+                        mbar_wait_sleep(smem_u32(&bars->acc_full), acc_seq & 1u, (uint32_t)p.sleep_ns);
                 }
                 for (int kb = 0; kb < p.L[0].kblocks; ++kb) {
                     mbar_expect_tx(smem_u32(&bars->in_full[kb]), (uint32_t)CH_IN_BYTES);
@@ -243,11 +251,13 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                         mbar_wait_cluster(smem_u32(&bars->a_full[kb]), (a_par >> kb) & 1u, 0u);
                         a_par ^= 1u << kb;
                         tc_fence_after();
+                        if (kb == 0 && img == cluster_id) CH_TRACE(7, l);
                         const uint32_t a_lo = a_lo0 + (uint32_t)kb * (CH_BLK >> 4);
                         for (int nh = 0; nh < L.nh; ++nh, ++seq) {
                             const uint32_t s = seq & (CH_SB - 1), ph = (seq / CH_SB) & 1u;
                             mbar_wait_cluster(smem_u32(&bars->b_full[s]), ph, 0u);
                             tc_fence_after();
+                            if (kb == 0 && nh == 0 && img == cluster_id) CH_TRACE(11, l);
                             const int n_ins = min(256, L.n_pad - nh * 256);
                             const uint32_t idesc = idesc_base | ((uint32_t)(n_ins >> 3) << 17);
                             const uint32_t b_lo = b_lo0 + s * (CH_B_STAGE >> 4);
@@ -260,6 +270,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                         }
                     }
                     umma2_commit_mc(smem_u32(&bars->acc_full));
+                    if (img == cluster_id) CH_TRACE(8, l);
                 }
         }
     } else {
@@ -292,6 +303,8 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
             for (int l = 0; l < p.n_layers; ++l, ++lseq) {
                 const ChainLayer& L = p.L[l];
                 const bool last = l == p.n_layers - 1;
+                const bool tr0 = it == 0 && warp == 0 && lane == 0, tr8 = it == 0 && warp == 8 && lane == 0;
+                if (tr0) CH_TRACE(0, l);
                 // ---------------- depthwise: K-blocks grp, grp + 2, ... ----------------
                 for (int kb = grp; kb < L.kblocks; kb += 2) {
                     uint8_t* blk = smem + CH_OFF_ACT + kb * CH_BLK;
@@ -336,6 +349,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
 #pragma unroll
                         for (int ox = 0; ox < 4; ++ox) o[oy][ox] = MF::template pack_act<RELU6>(ffma2_abc(acc[oy][ox], sc, bi));
                     __syncwarp();
+                    if (tr0 && kb == 0) CH_TRACE(1, l);
                     if (lane == 0) mbar_arrive(smem_u32(&bars->dwp_empty[ds]));
                     // all eight warps of this K-block have read their pixels: the block may now be overwritten by the operand tile
                     asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(256) : "memory");
@@ -349,10 +363,13 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                     if (lane == 0) mbar_arrive_cluster(leader_a_full0 + 8u * (uint32_t)kb);
                 }
                 dseq_base += (uint32_t)L.kblocks;
+                if (tr0) CH_TRACE(2, l);
+                if (tr8) CH_TRACE(9, l);
 
                 // ---------------- epilogue: accumulator -> next layer's activations (or global memory) ----------------
                 mbar_wait_sleep(smem_u32(&bars->acc_full), lseq & 1u, (uint32_t)p.sleep_ns);
                 tc_fence_after();
+                if (tr0) CH_TRACE(3, l);
                 const uint32_t as = lseq & 1u;
                 mbar_wait(smem_u32(&bars->aff_full[as]), (lseq >> 1) & 1u);
                 const float2* aff = reinterpret_cast<const float2*>(smem + CH_OFF_AFF + as * CH_AFF_BYTES);
@@ -394,6 +411,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                                 *reinterpret_cast<uint4*>(gout + cb * 32 + g * 8) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
                     }
                 }
+                if (tr0) CH_TRACE(4, l);
                 tc_fence_before();
                 if (!last) {
                     // padding slots the in-place operand tiles have overwritten: zero again for the next layer's depthwise
@@ -411,8 +429,10 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                 }
                 // every local worker has left the epilogue (TMEM drained, activations written) ...
                 asm volatile("bar.sync %0, %1;" ::"r"(3), "r"(CH_WORKERS * 32) : "memory");
+                if (tr0) CH_TRACE(5, l);
                 // ... and the peer has delivered my halo row
                 if (!last) { mbar_wait_cluster(smem_u32(&bars->halo_full), halo_seq & 1u, 0u); ++halo_seq; }
+                if (tr0) CH_TRACE(6, l);
             }
         }
     }
@@ -585,6 +605,23 @@ static int chain_launch_inst(ChainTcPlan* cp, cudaStream_t st) {
     FD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, cp->maps, cp->p));
     FD_CUDA_OK(cudaGetLastError());
     return FD_OK;
+}
+
+int chain_tc_launch(ChainTcPlan* cp, cudaStream_t st);
+// debug: run once with the timeline enabled; out_host[12 * 256] SM clocks of the leader CTA of cluster 0 (0 = slot unused)
+int chain_tc_trace(ChainTcPlan* cp, cudaStream_t st, unsigned long long* out_host, int* rows, int* cols) {
+    unsigned long long* dev = nullptr;
+    const size_t bytes = 12 * 256 * sizeof(unsigned long long);
+    FD_CUDA_OK(cudaMalloc(&dev, bytes));
+    FD_CUDA_OK(cudaMemsetAsync(dev, 0, bytes, st));
+    cp->p.trace = dev;
+    int rc = chain_tc_launch(cp, st);
+    cp->p.trace = nullptr;
+    if (rc == FD_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(FD_ERR_CUDA, "chain trace run failed");
+    if (rc == FD_OK) cudaMemcpy(out_host, dev, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(dev);
+    *rows = 12; *cols = 256;
+    return rc;
 }
 
 int chain_tc_launch(ChainTcPlan* cp, cudaStream_t st) {

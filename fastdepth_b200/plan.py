@@ -234,6 +234,16 @@ class Plan:
         _lib.check(self.lib.fd_plan_trace_stage(self.handle, stage, y.data_ptr(), stream_ptr, buf, 3072,
                                                 ctypes.byref(rows), ctypes.byref(cols)))
         a = np.frombuffer(buf, dtype=np.uint64).reshape(rows.value, cols.value).astype(np.int64)
+        in_chain = False
+        for st in self.steps():
+            if 'chain_tc' in st['kernel'] and '{stages ' in st['kernel']:
+                lo, hi = st['kernel'].split('{stages ')[1].rstrip('}').split('-')
+                in_chain = in_chain or int(lo) <= stage <= int(hi)
+        if in_chain:
+            cnames = ('layer_start', 'dw_first_kb_computed', 'dw_done_grp0', 'acc_full_seen', 'epilogue_done', 'local_barrier',
+                      'halo_received', 'mma_first_a_full', 'mma_last_commit', 'dw_done_grp1', 'tma_first_b_issue',
+                      'mma_first_b_full')
+            return {n: a[i][a[i] > 0] for i, n in enumerate(cnames)}
         names = ('tma_issue', 'dw_start', 'dw_math_done', 'a_published', 'mma_ready', 'mma_issued', 'epi_start', 'epi_done',
                  'epi_tmem_loaded', 'epi_staged', 'epi_barrier', 'epi_store_issued')
         return {n: a[i][a[i] > 0] for i, n in enumerate(names)}

@@ -35,7 +35,8 @@ def oracle():
 # only accumulation order and one-ulp rounding flips remain; flips propagate like fresh storage noise, so deep stages still
 # reach ~1.1e-2 on single elements (measured on B200: conv12/conv13 of the calm recipe) -- 2e-2 per stage, 4x sharper than the
 # 8e-2 the hot recipe needs against plain fp32, and the END-TO-END bound stays 1e-2
-EMUL_STAGE_TOL = {torch.float16: 2e-2, torch.bfloat16: 1.5e-1}
+EMUL_STAGE_TOL = {('calm', torch.float16): 2e-2, ('calm', torch.bfloat16): 1.5e-1,
+                  ('hot', torch.float16): 5e-2, ('hot', torch.bfloat16): 3e-1}     # measured maxima: 1.1e-2 / - / 3.1e-2 / 2.1e-1
 EMUL_FINAL_TOL = {torch.float16: 1e-2, torch.bfloat16: 8e-2}
 
 
@@ -318,6 +319,7 @@ def test_epilogue_organisations_and_item_shapes_agree_bitwise(widths, monkeypatc
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         eng = SkipAddEngine(m)
+        eng.set_option('chain', 0)                 # this test is about the per-block kernel's planner (conv7..11 included)
         for k, v in opts.items():
             eng.set_option(k, v)
         m.__dict__['_fd_engine'] = eng
@@ -375,7 +377,7 @@ def test_stage_by_stage_vs_storage_emulated_oracle(widths, recipe, dtype):
         got = plan.stage_tensor(i).float().cpu().permute(0, 3, 1, 2)
         assert got.shape == emu[name].shape, name
         worst[name] = rel_err(got, emu[name])
-    bad = {k: v for k, v in worst.items() if v > EMUL_STAGE_TOL[dtype]}
+    bad = {k: v for k, v in worst.items() if v > EMUL_STAGE_TOL[(recipe, dtype)]}
     assert not bad, bad
     assert rel_err(y.float().cpu(), want) <= EMUL_FINAL_TOL[dtype]
     if recipe == 'calm' and dtype == torch.float16:
