@@ -40,10 +40,13 @@ namespace fd {
 
 constexpr int TC_DW_WARPS = 8;
 constexpr int TC_EPI_WARPS = 8;
-#ifdef FD_TC_EPI_FIRST        // build-time A/B: which role gets the LOW warp ids (the warp scheduler's arbitration order depends on them)
-constexpr int TC_WARP_EPI0 = 0, TC_WARP_DW0 = TC_EPI_WARPS;  // epilogue 0..7 (warp % 4 == TMEM lane quarter), depthwise 8..15
-#else
+// Which role gets the LOW warp ids matters: the warp schedulers favour them when several warps are ready, and the epilogue
+// warps (few instructions, long dependent chains: TMEM load -> affine -> store -> fence -> barrier) were being starved by the
+// FMA streams of the depthwise warps.  Epilogue on warps 0..7: whole forward 610 -> 594 us (conv2 51 -> 46 us, conv1 58 -> 55 us).
+#ifdef FD_TC_DW_FIRST         // build-time A/B: the round-1 order
 constexpr int TC_WARP_EPI0 = TC_DW_WARPS, TC_WARP_DW0 = 0;   // depthwise 0..7, epilogue 8..15 (warp % 4 == TMEM lane quarter)
+#else
+constexpr int TC_WARP_EPI0 = 0, TC_WARP_DW0 = TC_EPI_WARPS;  // epilogue 0..7 (warp % 4 == TMEM lane quarter), depthwise 8..15
 #endif
 constexpr int TC_WARP_TMA = TC_DW_WARPS + TC_EPI_WARPS;      // 16
 constexpr int TC_WARP_MMA = TC_WARP_TMA + 1;                 // 17
@@ -490,42 +493,6 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                         asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory");
                     }
                     uint8_t* row = stg + m * 128;
-#ifdef FD_TC_EPI_PIPE
-                    // Build-time A/B: both 32-column halves of the block are requested from TMEM before the first is processed
-                    // (four 16-column loads, two register sets), so one TMEM round trip per block is exposed instead of two.
-                    {
-                        const int h0 = wide ? grp : 0, h1 = wide ? grp + 1 : 2;       // halves this warp handles
-                        uint32_t ra[16], rb[16];
-                        auto math16 = [&](uint32_t (&r)[16], int c16) {              // 16 columns at block-relative column c16
-#pragma unroll
-                            for (int g = 0; g < 2; ++g) {
-                                uint32_t pk[4];
-                                float4 af[4];
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) af[j] = *reinterpret_cast<const float4*>(aff + cb * 64 + c16 + g * 8 + 2 * j);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    pk[j] = MF::template pack_act<RELU6>(ffma2_abc(
-                                        f32x2_make(__uint_as_float(r[g * 8 + 2 * j]), __uint_as_float(r[g * 8 + 2 * j + 1])),
-                                        f32x2_make(af[j].x, af[j].y), f32x2_make(af[j].z, af[j].w)));
-                                *reinterpret_cast<uint4*>(row + ((((c16 >> 3) + g) ^ (m & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                            }
-                        };
-                        const int c_first = h0 * 32, c_end = min(h1 * 32, p.n_cta - cb * 64);    // n_cta is a multiple of 16
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) rb[j] = 0u;
-                        if (c_first < c_end) tmem_ld16_issue16(t_lane + cb * 64 + c_first, ra);
-                        for (int c = c_first; c < c_end; c += 32) {
-                            const bool two = c + 16 < c_end;
-                            if (two) tmem_ld16_issue16(t_lane + cb * 64 + c + 16, rb);
-                            tmem_ld_wait16x2(ra, rb);
-                            if (grp == 0 && elected && cb == 0 && c == c_first) TC_TRACE(8, tr);
-                            math16(ra, c);
-                            if (c + 32 < c_end) tmem_ld16_issue16(t_lane + cb * 64 + c + 32, ra);   // in flight during the math below
-                            if (two) math16(rb, c + 16);
-                        }
-                    }
-#else
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         const int col0 = cb * 64 + half * 32;             // first accumulator column of this half block
@@ -551,7 +518,6 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                             }
                         }
                     }
-#endif
                     if (cb == cb_last) {                                  // last TMEM read of this item: release the accumulator early
                         tc_fence_before();
                         __syncwarp();

@@ -59,6 +59,7 @@ struct ChainBarriers {
     uint64_t aff_full[2], aff_empty[2];
     uint64_t acc_full;                  // tcgen05.commit multicast: all MMAs of the layer done
     uint64_t halo_full;                 // 16 remote arrivals: the peer has written my halo row of the next layer
+    uint64_t act_free;                  // the last layer's output has left the activation blocks (TMA stores have read them)
     uint32_t tmem_base, pad;
 };
 constexpr int CH_SMEM_BYTES = CH_OFF_BAR + (int)sizeof(ChainBarriers) + 1024;     // + alignment slack
@@ -90,6 +91,8 @@ struct ChainParams {
 struct ChainMaps {
     CUtensorMap in;                    // first layer's input, NHWC as (C, W, H, N), box (64, 15, 9, 1), SWIZZLE_128B, OOB -> 0
     CUtensorMap w[CH_MAX_LAYERS];      // pointwise weights [c_out][c_in] as (K, N), box (64, 128), SWIZZLE_128B
+    CUtensorMap out[2];                // last layer's output, NHWC as (C, W, H, N), per cluster rank: box (64, 15, rows of that rank, 1),
+                                       // SWIZZLE_128B; column 14 and channels >= c_out are clipped by the hardware
 };
 
 // ---- cluster / 2-CTA PTX -------------------------------------------------------------------------------
@@ -165,6 +168,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->aff_full[i]), 1); mbar_init(smem_u32(&bars->aff_empty[i]), CH_WORKERS); }
         mbar_init(smem_u32(&bars->acc_full), 1);
         mbar_init(smem_u32(&bars->halo_full), CH_WORKERS);
+        mbar_init(smem_u32(&bars->act_free), 1);
         fence_barrier_init();
     }
     // every activation slot starts as finite zeros (padding, channels a narrower layer never writes)
@@ -173,6 +177,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
     if (warp == CH_WARP_MMA) tmem_alloc_2cta(smem_u32(&bars->tmem_base), 512u);
     if (warp == CH_WARP_TMA && lane == 0) {
         tma_prefetch_desc(&maps.in);
+        tma_prefetch_desc(&maps.out[rank]);
         for (int l = 0; l < p.n_layers; ++l) tma_prefetch_desc(&maps.w[l]);
     }
     pdl_launch_dependents();
@@ -224,14 +229,10 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                 }
         } else if (lane == 2) {
             // the first layer's input: one box per K-block, rows row_first - 1 .. + 7 (OOB rows / column 14 arrive as zeros)
-            uint32_t it = 0, acc_seq = 0;
+            uint32_t it = 0;
             for (int img = cluster_id; img < p.n_img; img += n_clusters, ++it) {
-                if (it > 0) {
-                    // the activation blocks are free once the previous image's LAST layer has finished its MMAs: follow the
-                    // accumulator barrier through every layer's phase (a parity alone cannot tell phase 0 from phase 4)
-                    for (int l = 0; l < p.n_layers; ++l, ++acc_seq)
-                        mbar_wait_sleep(smem_u32(&bars->acc_full), acc_seq & 1u, (uint32_t)p.sleep_ns);
-                }
+                // the activation blocks are free once the previous image's output tiles have been read out of them
+                if (it > 0) mbar_wait_sleep(smem_u32(&bars->act_free), (it - 1u) & 1u, (uint32_t)p.sleep_ns);
                 for (int kb = 0; kb < p.L[0].kblocks; ++kb) {
                     mbar_expect_tx(smem_u32(&bars->in_full[kb]), (uint32_t)CH_IN_BYTES);
                     tma_load_4d(smem_base + CH_OFF_ACT + kb * CH_BLK, &maps.in, smem_u32(&bars->in_full[kb]), kb * 64, 0, row_first - 1, img);
@@ -276,16 +277,24 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
     } else {
         // =========================== workers: depthwise, then epilogue, per layer ===========================
         const int grp = warp >> 3, wi = warp & 7;
-        const int ty0 = (wi >> 2) * 4, tx0 = (wi & 3) * 4;                 // this warp's 4x4 pixel block of the 8x16 slot tile
-        const int s0 = ty0 * CH_PITCH + tx0 - 1;                            // slot of its top-left input pixel (-1: the spare zero slot)
+        // Depthwise mapping: a CTA owns at most 7 rows x 14 columns, so warp wi < 7 computes the two columns 2 wi, 2 wi + 1 of
+        // all seven rows (14 outputs from a 9 x 4 input patch; every computed pixel can be a real one) and the eighth warp of the
+        // group only takes part in the hand-shakes.  (A 4x4-blocks-of-an-8x16-tile mapping spends 23 % of its FMAs on slots
+        // that are never pixels and was measured at 4 800 cycles per K-block pair.)
+        const bool dw_active = wi < 7;
+        const int tx0 = 2 * (dw_active ? wi : 0);
+        const int s0 = tx0 - 1;                                             // slot of the patch's top-left pixel (-1: the spare zero slot)
         // lane = channel pair; 16-byte chunk (lane >> 2) lives at chunk position (lane >> 2) ^ (slot & 7): one byte offset per
         // residue of the slot index modulo 8, rotated so that a compile-time slot offset k selects rd_off[k & 7]
         uint32_t rd_off[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) rd_off[j] = ((((uint32_t)lane >> 2) ^ ((uint32_t)(s0 + j) & 7u)) << 4) + (((uint32_t)lane & 3u) << 2);
-        uint32_t wr_off[4];                                                 // operand row m = ty * 16 + tx: m & 7 == (tx0 & 4) + ox
+        uint32_t wr_off[2];                                                 // operand row m = ty * 16 + tx: m & 7 == (tx0 + ox) & 7
 #pragma unroll
-        for (int ox = 0; ox < 4; ++ox) wr_off[ox] = ((((uint32_t)lane >> 2) ^ (uint32_t)((tx0 & 4) + ox)) << 4) + (((uint32_t)lane & 3u) << 2);
+        for (int ox = 0; ox < 2; ++ox) wr_off[ox] = ((((uint32_t)lane >> 2) ^ ((uint32_t)(tx0 + ox) & 7u)) << 4) + (((uint32_t)lane & 3u) << 2);
+        // zero list: thread t < n_zero * 8 re-zeroes 16-byte chunk (t & 7) of slot zero_slots[t >> 3] in every K-block
+        const int nzc = p.n_zero[rank] * 8;
+        const uint32_t z_off = (int)threadIdx.x < nzc ? (uint32_t)p.zero_slots[rank][threadIdx.x >> 3] * 128u + ((uint32_t)threadIdx.x & 7u) * 16u : 0u;
         // epilogue role: TMEM lane quarter q = warp % 4, 32-column blocks cq, cq + 4, ...; thread = pixel slot m
         const int q = warp & 3, cq = warp >> 2;
         const int m = q * 32 + lane, e_ty = m >> 4, e_tx = m & 15;
@@ -315,49 +324,51 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                     const f32x2 sc = *reinterpret_cast<const f32x2*>(prm + 9 * 128 + lane * 8);
                     const f32x2 bi = *reinterpret_cast<const f32x2*>(prm + 9 * 128 + 256 + lane * 8);
                     const uint8_t* in0 = blk + s0 * 128;
-                    f32x2 acc[4][4];
+                    uint32_t o[7][2];
+                    if (dw_active) {
+                        f32x2 acc[7][2];
 #pragma unroll
-                    for (int a = 0; a < 4; ++a)
+                        for (int a = 0; a < 7; ++a) acc[a][0] = acc[a][1] = 0ull;
+                        f32x2 wq[3][3];
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) acc[a][b] = 0ull;
-                    f32x2 wq[3][3];
+                        for (int iy = 0; iy < 9; ++iy) {
+                            if (iy < 3) {
 #pragma unroll
-                    for (int iy = 0; iy < 6; ++iy) {
-                        if (iy < 3) {
+                                for (int kx = 0; kx < 3; ++kx) wq[iy][kx] = MF::widen(*reinterpret_cast<const uint32_t*>(prm + (iy * 3 + kx) * 128 + lane * 4));
+                            }
+                            f32x2 row[4];
 #pragma unroll
-                            for (int kx = 0; kx < 3; ++kx) wq[iy][kx] = MF::widen(*reinterpret_cast<const uint32_t*>(prm + (iy * 3 + kx) * 128 + lane * 4));
+                            for (int ix = 0; ix < 4; ++ix) {
+                                const int k = iy * CH_PITCH + ix;
+                                row[ix] = MF::widen(*reinterpret_cast<const uint32_t*>(in0 + k * 128 + rd_off[k & 7]));
+                            }
+#pragma unroll
+                            for (int oy = 0; oy < 7; ++oy) {
+                                const int ky = iy - oy;
+                                if (ky < 0 || ky >= 3) continue;
+#pragma unroll
+                                for (int ox = 0; ox < 2; ++ox)
+#pragma unroll
+                                    for (int kx = 0; kx < 3; ++kx) ffma2(acc[oy][ox], row[ox + kx], wq[ky][kx]);
+                            }
                         }
-                        f32x2 row[6];
 #pragma unroll
-                        for (int ix = 0; ix < 6; ++ix) {
-                            const int k = iy * CH_PITCH + ix;
-                            row[ix] = MF::widen(*reinterpret_cast<const uint32_t*>(in0 + k * 128 + rd_off[k & 7]));
-                        }
+                        for (int oy = 0; oy < 7; ++oy)
 #pragma unroll
-                        for (int oy = 0; oy < 4; ++oy) {
-                            const int ky = iy - oy;
-                            if (ky < 0 || ky >= 3) continue;
-#pragma unroll
-                            for (int ox = 0; ox < 4; ++ox)
-#pragma unroll
-                                for (int kx = 0; kx < 3; ++kx) ffma2(acc[oy][ox], row[ox + kx], wq[ky][kx]);
-                        }
+                            for (int ox = 0; ox < 2; ++ox) o[oy][ox] = MF::template pack_act<RELU6>(ffma2_abc(acc[oy][ox], sc, bi));
                     }
-                    uint32_t o[4][4];
-#pragma unroll
-                    for (int oy = 0; oy < 4; ++oy)
-#pragma unroll
-                        for (int ox = 0; ox < 4; ++ox) o[oy][ox] = MF::template pack_act<RELU6>(ffma2_abc(acc[oy][ox], sc, bi));
                     __syncwarp();
                     if (tr0 && kb == 0) CH_TRACE(1, l);
                     if (lane == 0) mbar_arrive(smem_u32(&bars->dwp_empty[ds]));
                     // all eight warps of this K-block have read their pixels: the block may now be overwritten by the operand tile
                     asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(256) : "memory");
+                    if (dw_active) {
 #pragma unroll
-                    for (int oy = 0; oy < 4; ++oy)
+                        for (int oy = 0; oy < 7; ++oy)
 #pragma unroll
-                        for (int ox = 0; ox < 4; ++ox)
-                            *reinterpret_cast<uint32_t*>(blk + ((ty0 + oy) * 16 + tx0 + ox) * 128 + wr_off[ox]) = o[oy][ox];
+                            for (int ox = 0; ox < 2; ++ox)
+                                *reinterpret_cast<uint32_t*>(blk + (oy * 16 + tx0 + ox) * 128 + wr_off[ox]) = o[oy][ox];
+                    }
                     fence_proxy_async();                       // generic-proxy writes -> visible to the tensor cores (async proxy)
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(leader_a_full0 + 8u * (uint32_t)kb);
@@ -375,9 +386,9 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                 const float2* aff = reinterpret_cast<const float2*>(smem + CH_OFF_AFF + as * CH_AFF_BYTES);
                 const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
                 const int ncb = L.n_pad >> 5;
-                T* gout = nullptr;
-                if (last && e_valid)
-                    gout = reinterpret_cast<T*>(p.out) + ((size_t)(img * p.h + row_first + e_ty) * p.w + e_tx) * p.out_pitch;
+                // the last layer's tile is staged in the (now dead) activation blocks from slot 0 on -- a 1 KB-aligned TMA source --
+                // and leaves through tensor stores; every other layer writes the next layer's input rows 1.. and the peer's halo
+                const int w_slot = last ? e_ty * CH_PITCH + e_tx : e_slot;
                 for (int cb = cq; cb < ncb; cb += 4) {
                     uint32_t r[32];
                     tmem_ld32_sync(t_lane + (uint32_t)(cb * 32), r);
@@ -388,37 +399,30 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                         pk[j] = MF::template pack_act<RELU6>(ffma2_abc(f32x2_make(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])),
                                                                         f32x2_make(af.x, af.y), f32x2_make(af.z, af.w)));
                     }
-                    if (!last) {
-                        const uint32_t boff = (uint32_t)(cb >> 1) * CH_BLK, c4 = (uint32_t)(cb & 1) * 4u;
-                        if (e_valid) {
-                            uint8_t* dst = smem + CH_OFF_ACT + boff + e_slot * 128;
-#pragma unroll
-                            for (int g = 0; g < 4; ++g)
-                                *reinterpret_cast<uint4*>(dst + (((c4 + g) ^ ((uint32_t)e_slot & 7u)) << 4)) =
-                                    make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-                        }
-                        if (e_halo) {
-                            const uint32_t dst = peer_act + boff + (uint32_t)e_halo_slot * 128u;
-#pragma unroll
-                            for (int g = 0; g < 4; ++g)
-                                st_cluster_v4(dst + (((c4 + g) ^ ((uint32_t)e_halo_slot & 7u)) << 4),
-                                              make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]));
-                        }
-                    } else if (gout != nullptr) {
+                    const uint32_t boff = (uint32_t)(cb >> 1) * CH_BLK, c4 = (uint32_t)(cb & 1) * 4u;
+                    if (e_valid) {
+                        uint8_t* dst = smem + CH_OFF_ACT + boff + w_slot * 128;
 #pragma unroll
                         for (int g = 0; g < 4; ++g)
-                            if (cb * 32 + g * 8 < L.c_out)        // c_out is a multiple of 8: whole 16-byte chunks
-                                *reinterpret_cast<uint4*>(gout + cb * 32 + g * 8) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+                            *reinterpret_cast<uint4*>(dst + (((c4 + g) ^ ((uint32_t)w_slot & 7u)) << 4)) =
+                                make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+                    }
+                    if (e_halo && !last) {
+                        const uint32_t dst = peer_act + boff + (uint32_t)e_halo_slot * 128u;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            st_cluster_v4(dst + (((c4 + g) ^ ((uint32_t)e_halo_slot & 7u)) << 4),
+                                          make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]));
                     }
                 }
                 if (tr0) CH_TRACE(4, l);
                 tc_fence_before();
                 if (!last) {
                     // padding slots the in-place operand tiles have overwritten: zero again for the next layer's depthwise
-                    const int nz = p.n_zero[rank], kbn = p.L[l + 1].kblocks;
-                    for (int i = threadIdx.x; i < nz * kbn * 8; i += CH_WORKERS * 32) {
-                        const int ch = i & 7, zi = (i >> 3) % nz, kb = (i >> 3) / nz;
-                        *reinterpret_cast<uint4*>(smem + CH_OFF_ACT + kb * CH_BLK + (int)p.zero_slots[rank][zi] * 128 + ch * 16) = make_uint4(0u, 0u, 0u, 0u);
+                    if ((int)threadIdx.x < nzc) {
+                        const int kbn = p.L[l + 1].kblocks;
+                        for (int kb = 0; kb < kbn; ++kb)
+                            *reinterpret_cast<uint4*>(smem + CH_OFF_ACT + kb * CH_BLK + z_off) = make_uint4(0u, 0u, 0u, 0u);
                     }
                 }
                 fence_proxy_async();        // these generic-proxy writes precede async-proxy accesses (MMA reads, the next image's TMA)
@@ -432,9 +436,18 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                 if (tr0) CH_TRACE(5, l);
                 // ... and the peer has delivered my halo row
                 if (!last) { mbar_wait_cluster(smem_u32(&bars->halo_full), halo_seq & 1u, 0u); ++halo_seq; }
+                if (last && threadIdx.x == 0) {
+                    // every worker's staging writes are complete (barrier above) and fenced towards the async proxy
+                    for (int kb = 0; kb < (L.c_out + 63) / 64; ++kb)
+                        tma_store_4d(&maps.out[rank], smem_base + CH_OFF_ACT + kb * CH_BLK, kb * 64, 0, row_first, img);
+                    bulk_commit_group();
+                    bulk_wait_read0();                                    // the blocks may be refilled with the next image
+                    mbar_arrive(smem_u32(&bars->act_free));
+                }
                 if (tr0) CH_TRACE(6, l);
             }
         }
+        if (threadIdx.x == 0) bulk_wait_all();     // the output tiles have landed in global memory
     }
 
     __syncwarp();
@@ -574,6 +587,17 @@ int chain_tc_prepare(int dtype, const BlockArgs* layers, int n_layers, const TcL
         CUresult r = encode(&cp->maps.in, dt, 4, const_cast<void*>(layers[0].in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) rc = fail(FD_ERR_CUDA, "cuTensorMapEncodeTiled(chain input) failed: " + std::to_string((int)r));
+    }
+    for (int r = 0; r < 2 && rc == FD_OK; ++r) {
+        const int rows_r = r == 0 ? p.rows0 : p.h - p.rows0;
+        const cuuint64_t P = (cuuint64_t)p.out_pitch;
+        cuuint64_t dims[4] = {(cuuint64_t)gl.c_out, (cuuint64_t)gl.w_out, (cuuint64_t)gl.h_out, (cuuint64_t)gl.n};
+        cuuint64_t strides[3] = {P * es, (cuuint64_t)gl.w_out * P * es, (cuuint64_t)gl.h_out * gl.w_out * P * es};
+        cuuint32_t box[4] = {64, (cuuint32_t)CH_PITCH, (cuuint32_t)rows_r, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult cr = encode(&cp->maps.out[r], dt, 4, p.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) rc = fail(FD_ERR_CUDA, "cuTensorMapEncodeTiled(chain output) failed: " + std::to_string((int)cr));
     }
     if (rc != FD_OK) { chain_tc_destroy(cp); return rc; }
     const int clusters = std::min(p.n_img, std::max(1, opts.n_sms / 2));

@@ -1,0 +1,11 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "chain_kernel" --timeout 120 > gpurun_out/c4_chain.txt 2>&1; echo "chain rc=$?" >> gpurun_out/c4_chain.txt
+tail -n 4 gpurun_out/c4_chain.txt
+timeout 200 python tools/trace_chain.py > gpurun_out/c4_trace_chain.txt 2>&1; cat gpurun_out/c4_trace_chain.txt
+timeout 300 python tools/ab_matrix.py stock '' > gpurun_out/c4_ab.txt 2>&1
+timeout 300 python tools/ab_matrix.py pruned '' >> gpurun_out/c4_ab.txt 2>&1
+cat gpurun_out/c4_ab.txt
+timeout 1800 python -m pytest tests -m gpu -q --timeout 600 --deselect tests/test_gpu_parity.py::test_chain_kernel_matches_per_layer_kernels > gpurun_out/c4_pytest.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/c4_pytest.txt
+tail -n 6 gpurun_out/c4_pytest.txt
