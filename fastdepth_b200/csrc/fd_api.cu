@@ -105,6 +105,7 @@ struct fd_plan {
     bool steps_valid = false;
     int opt_path = 1, opt_fold_head = 1, opt_graph = 1, opt_tma_epilogue = 1, opt_inplace_skip = 1, opt_pdl = 1, opt_wait_sleep_ns = 0;
     int opt_chain = 1;
+    int opt_cluster = 1;
     size_t workspace_bytes = 0;
     // fd_pipeline_*: host batches flow H2D -> forward -> D2H through kPipeSlots device slots on three streams
     struct PipeSlot { void* x = nullptr; void* y = nullptr; cudaEvent_t up = nullptr, done = nullptr, down = nullptr; bool busy = false; };
@@ -183,7 +184,7 @@ static int build_steps(fd_plan* p) {
         if (!s.have_weights) return fail(FD_ERR_STATE, "fd_plan_set_stage_weights was not called for every stage");
 
     TcLaunchOpts lopts;                   // every kernel plan keeps its own copy (no process-wide launch state)
-    lopts.pdl = p->opt_pdl; lopts.sleep_ns = p->opt_wait_sleep_ns; lopts.n_sms = p->n_sms;
+    lopts.pdl = p->opt_pdl; lopts.sleep_ns = p->opt_wait_sleep_ns; lopts.n_sms = p->n_sms; lopts.cluster = p->opt_cluster;
     Stage& head = p->stages[ns - 1];
     Stage& last = p->stages[ns - 2];
     // decode_conv6 below the last upsample: exact because a 1x1 conv, a per-channel affine and ReLU
@@ -356,7 +357,7 @@ static int build_steps(fd_plan* p) {
 static int run_steps(fd_plan* p, const void* x, void* y, cudaStream_t st) {
     for (auto& s : p->steps) {
         int rc = s.run(st, x, y);
-        if (rc != FD_OK) return rc;
+        if (rc != FD_OK) return fail(rc, std::string(fd_last_error()) + " [stage " + std::to_string(s.stage) + ": " + s.name + "]");
     }
     return FD_OK;
 }
@@ -519,6 +520,7 @@ static int* option_slot(fd_plan* p, const char* name) {
     if (!strcmp(name, "pdl")) return &p->opt_pdl;
     if (!strcmp(name, "wait_sleep_ns")) return &p->opt_wait_sleep_ns;
     if (!strcmp(name, "chain")) return &p->opt_chain;
+    if (!strcmp(name, "cluster")) return &p->opt_cluster;
     return nullptr;
 }
 
@@ -795,6 +797,7 @@ int fd_debug_block_plan(int ksize, int stride, int h_out, int w_out, int n, int 
     for (int i = 0; i < 16; ++i) out[i] = v[i];
     if (cap >= 18) { out[16] = q.nacc; out[17] = q.epi_colsplit; }
     if (cap >= 19) out[18] = q.epi_wide;
+    if (cap >= 20) out[19] = q.cs;
     return FD_OK;
 }
 

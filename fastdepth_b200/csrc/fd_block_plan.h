@@ -8,6 +8,7 @@ constexpr int kPlanKblk = 64;
 constexpr int kPlanAStage = 128 * 128;       // one A operand stage: 128 rows x 64 x 2 B
 constexpr int kPlanStg = 16384;              // one epilogue staging tile: 128 px x 64 ch x 2 B
 constexpr int kPlanMaxIn = 6, kPlanMaxA = 4, kPlanMaxB = 16;
+constexpr int kPlanMaxACluster = 6;          // cluster mode: the A ring is filled by several CTAs at once and wants >= cluster size stages
 constexpr int kPlanSmemBudget = 224 * 1024;  // of the 227 KB a CTA may use (alignment slack is budgeted separately)
 
 struct BlockPlanIn {
@@ -19,6 +20,8 @@ struct BlockPlanIn {
     int no_wide;                 // experiments: 1 = a single epilogue group stays four warps (FD_TC_NO_WIDE)
     int no_colsplit;             // experiments: 1 = epilogue groups take alternate items even when they could share (FD_TC_NO_COLSPLIT)
     int n_sms;                   // SMs of the device (one CTA each); 0 = 148 (B200)
+    int cluster;                 // 0 = the cost model may choose cluster mode, 1 = never, 2 / 4 = force that cluster size when the
+                                 // block admits it (plan option "cluster", FD_TC_CLUSTER)
 };
 struct BlockPlanOut {
     int ok;
@@ -29,6 +32,9 @@ struct BlockPlanOut {
     int nacc;                    // TMEM accumulators: 2 of n_cta <= 256 columns, or 1 of up to 512
     int epi_colsplit;            // 1: both epilogue groups drain every item, alternating 64-column blocks
     int epi_wide;                // 1: one staging tile, all eight epilogue warps on it (32 columns per warp)
+    int cs;                      // cluster size: 1, or 2 / 4 CTAs that share one tile -- CTA r computes the depthwise half of the
+                                 // K-blocks kb % cs == r, broadcasts its operand tiles to the others through DSMEM and runs the MMAs
+                                 // of output-channel split r (splits == cs)
     int smem_bytes;
 };
 
@@ -43,7 +49,8 @@ inline bool plan_block_smem(const BlockPlanIn& q, BlockPlanOut& p, bool allow_na
     long best = -(1L << 60);
     bool found = false;
     const int bn_top = p.n_cta < 256 ? p.n_cta : 256;
-    for (int s_a = kPlanMaxA; s_a >= 2; --s_a)
+    const int per_cta_kb = p.cs > 1 ? (p.kblocks + p.cs - 1) / p.cs : p.kblocks;      // K-blocks whose input tile THIS CTA loads
+    for (int s_a = p.cs > 1 ? kPlanMaxACluster : kPlanMaxA; s_a >= 2; --s_a)
         for (int eg = q.head ? 1 : 3; eg >= 0; --eg) {
             // epilogue organisation: 3 = two groups x two tiles, 2 = two groups x one tile, 1 = one group x two, 0 = one x one
             const int groups = q.head ? 2 : (eg >= 2 ? 2 : 1);
@@ -63,6 +70,7 @@ inline bool plan_block_smem(const BlockPlanIn& q, BlockPlanOut& p, bool allow_na
                         int s_in = left / p.in_stage_stride;
                         if (s_in > kPlanMaxIn) s_in = kPlanMaxIn;
                         if (s_in < 2 && !(s_in == 1 && p.kblocks == 1 && p.items <= sms)) continue;
+                        if (p.cs > 1 && s_in > per_cta_kb + 1) s_in = per_cta_kb + 1 < 2 ? 2 : per_cta_kb + 1;
                         const int bn_eff = bn < 128 ? bn : 128;
                         // weight ring depth in K-blocks: below 2 the MMA of K-block k+1 waits for a weight load that could
                         // only start when the MMA of K-block k had finished (measured: conv7 lost a third of its time there)
@@ -73,6 +81,9 @@ inline bool plan_block_smem(const BlockPlanIn& q, BlockPlanOut& p, bool allow_na
                         if (p.n_cta > 256)       // 64 KB of weights per K-block: the weight ring needs the room more than the input ring
                             score = (long)bn_eff * 100 + (bn >= 256 ? 500 : 0) + (s_in > 3 ? 3 : s_in) * 2500 + s_a * 400 + n_stg * 300 +
                                     b_ahead2 * 3000;
+                        if (p.cs > 1)        // every CTA of the cluster produces operand tiles concurrently: one stage each, plus slack
+                            score = (long)bn_eff * 100 + (bn >= 256 ? 500 : 0) + (s_in > 3 ? 3 : s_in) * 1500 +
+                                    (s_a > p.cs + 1 ? p.cs + 1 : s_a) * 4000 + groups * 2500 + n_stg * 300 + b_ahead2 * 2500;
                         if (bn < 64 && bn < bn_top) {                        // narrow MMAs are a last resort
                             if (!allow_narrow) continue;
                             score -= 20000;
@@ -118,11 +129,11 @@ inline BlockPlanOut plan_block(const BlockPlanIn& q) {
     // is chip-wide: the L2 delivers ~6300 B/clk to all SMs together (B300_MICROARCH.md), ~5500 sustained here, and the
     // 14x14 blocks sit on it (conv7: 148 CTAs x 57 KB per K-block every 1750 cycles).
     const int cout_pad = (q.c_out + 15) / 16 * 16;
-    struct Cand { long t; int sp, nc; };
-    Cand cands[8];
+    struct Cand { long t; int sp, nc, cs; };
+    Cand cands[12];
     int n_cands = 0;
     if (cout_pad <= 64 || q.head) {
-        cands[n_cands++] = Cand{0, 1, cout_pad};
+        cands[n_cands++] = Cand{0, 1, cout_pad, 1};
     } else {
         const long dw_c = q.ksize == 5 ? 2100 : (q.stride == 2 ? 1200 : 1000);
         for (int n_cta = 512; n_cta >= 64; n_cta -= 64) {
@@ -144,11 +155,37 @@ inline BlockPlanOut plan_block(const BlockPlanIn& q) {
             const long t = rounds * p.kblocks * (kb_c + 100) + drain;
             int at = n_cands++;
             while (at > 0 && cands[at - 1].t > t) { cands[at] = cands[at - 1]; --at; }
-            cands[at] = Cand{t, sp, nc};
+            cands[at] = Cand{t, sp, nc, 1};
+        }
+        // Cluster mode: cs CTAs share one tile.  Without it every output-channel split recomputes the whole depthwise half
+        // (conv13: 4 splits x 16 K-blocks of depthwise per CTA against 8 K-blocks' worth of MMA time); with it the depthwise
+        // work of a tile is divided by cs and the K loop runs at the MMA's pace.
+        // Measured (profiles/r02_cluster_ab.txt, stock and pruned widths at batch 64): the hand-over latency and the start-up of a
+        // cluster eat the gain everywhere except on the 7x7 maps with a 5x5 depthwise (decode_conv1: 36.1 -> 32.2 us; the
+        // 3x3 blocks there stay paced by their weight stream), so the automatic choice is limited to that case; the plan
+        // option / FD_TC_CLUSTER = 2 | 4 forces it wherever the block admits it (the bitwise tests do).
+        for (int cs = 2; cs <= 4 && q.cluster != 1; cs *= 2) {
+            if (q.cluster > 1 && q.cluster != cs) continue;
+            if (q.cluster == 0 && !(q.ksize == 5 && q.tile == 1 && cs == 4 && (long)q.n_tiles * cs <= sms)) continue;
+            const int nc = ((cout_pad + cs - 1) / cs + 63) / 64 * 64;
+            if (nc > 256 || nc * (cs - 1) >= cout_pad || p.kblocks < cs) continue;      // every CTA owns >= 1 K-block and a non-empty split
+            const long n_cl = sms / cs;
+            const long rounds = ((long)q.n_tiles + n_cl - 1) / n_cl;
+            const long mma_c = 2L * nc;
+            const long active = (q.n_tiles < n_cl ? q.n_tiles : n_cl) * cs;
+            const long l2_c = active * (p.in_stage_bytes / cs + 128L * nc) / 5500;
+            long kb_c = dw_c / cs > mma_c ? dw_c / cs : mma_c;
+            if (l2_c > kb_c) kb_c = l2_c;
+            const long drain = (nc > 64 ? 23L : 45L) * nc;
+            long t = rounds * p.kblocks * (kb_c + 150) + drain + 1500;                   // + cluster start-up and hand-over latency
+            if (q.cluster > 1) t = -1;                                                   // forced
+            int at = n_cands++;
+            while (at > 0 && cands[at - 1].t > t) { cands[at] = cands[at - 1]; --at; }
+            cands[at] = Cand{t, cs, nc, cs};
         }
     }
     for (int i = 0; i < n_cands; ++i) {
-        p.splits = cands[i].sp; p.n_cta = cands[i].nc;
+        p.splits = cands[i].sp; p.n_cta = cands[i].nc; p.cs = cands[i].cs;
         p.items = q.n_tiles * p.splits;
         p.cpad_all = p.n_cta * p.splits;
         p.nacc = p.n_cta > 256 ? 1 : 2;
@@ -157,7 +194,7 @@ inline BlockPlanOut plan_block(const BlockPlanIn& q) {
         if (plan_block_smem(q, p, false)) { p.ok = 1; return p; }
     }
     for (int i = 0; i < n_cands; ++i) {                              // nothing fits with full-width MMAs: accept narrow ones
-        p.splits = cands[i].sp; p.n_cta = cands[i].nc;
+        p.splits = cands[i].sp; p.n_cta = cands[i].nc; p.cs = cands[i].cs;
         p.items = q.n_tiles * p.splits;
         p.cpad_all = p.n_cta * p.splits;
         p.nacc = p.n_cta > 256 ? 1 : 2;

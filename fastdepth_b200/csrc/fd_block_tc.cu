@@ -51,9 +51,12 @@ constexpr int TC_WARP_EPI0 = 0, TC_WARP_DW0 = TC_EPI_WARPS;  // epilogue 0..7 (w
 constexpr int TC_WARP_TMA = TC_DW_WARPS + TC_EPI_WARPS;      // 16
 constexpr int TC_WARP_MMA = TC_WARP_TMA + 1;                 // 17
 constexpr int TC_THREADS = (TC_WARP_MMA + 1) * 32;           // 576
+constexpr int TC_WARP_BCAST = TC_WARP_MMA + 1;               // 18: cluster mode only -- hands finished operand tiles to the peer CTAs
+constexpr int TC_THREADS_CL = (TC_WARP_BCAST + 1) * 32;      // 608 (19 warps x 96 registers still fit the register file)
 constexpr int TC_KBLK = 64;                     // channels per K-block (one 128-byte swizzle row)
 constexpr int TC_A_STAGE_BYTES = 128 * 128;     // 128 rows x 64 x 2 B
-constexpr int TC_MAX_IN = 6, TC_MAX_A = 4, TC_MAX_B = 16;
+constexpr int TC_MAX_IN = 6, TC_MAX_A = 6, TC_MAX_B = 16;
+static_assert(TC_MAX_A >= kPlanMaxACluster && TC_MAX_A >= kPlanMaxA && TC_MAX_IN >= kPlanMaxIn && TC_MAX_B >= kPlanMaxB, "barrier arrays cover the planner's ring depths");
 constexpr int TC_TRACE_N = 256;
 
 struct TcParams {
@@ -98,6 +101,15 @@ struct TcParams {
     const void* dwp;      // [kblocks] x { [k*k][64] 16-bit taps, [64] fp32 scale, [64] fp32 bias }
     const float2* pw_affine;  // [cpad_all / 2] x (scale, scale, bias, bias) of a channel pair
     const float* head_w;  // [cpad_all]
+    int cl_debug;         // bring-up: bit 0 = commit a_empty locally only (no multicast; flow control of the A ring is then unsafe)
+    int epi_high;         // 1: the epilogue runs on warps 8..15 and the depthwise on 0..7 (default: the other way round).  Which role
+                          // the schedulers' arbitration should favour depends on which one paces the block: the stride-2 blocks are
+                          // paced by their single epilogue staging tile, the others by the depthwise
+    int wmc;              // weight-multicast cluster size (1, 2, 4): the wmc CTAs of a cluster take wmc consecutive tiles with the SAME
+                          // output-channel split and each loads 1/wmc of every weight block, TMA-multicast into all of them
+    int cs;               // cluster size (1, 2, 4): the cs CTAs of a cluster work on the SAME tile (splits == cs); CTA r computes the
+                          // depthwise half of the K-blocks kb % cs == r only and broadcasts each finished operand tile into the A
+                          // ring of every CTA of the cluster (bulk copies over DSMEM), then runs the MMAs of output-channel split r
     unsigned long long* trace;   // debug timeline (fd_plan_trace_stage) or nullptr: [12 rows][TC_TRACE_N] SM clocks of CTA 0
 };
 
@@ -107,6 +119,7 @@ struct TcBarriers {
     uint64_t a_full[TC_MAX_A], a_empty[TC_MAX_A];
     uint64_t b_full[TC_MAX_B], b_empty[TC_MAX_B];
     uint64_t acc_full[2], acc_empty[2];
+    uint64_t dw_done[4];  // cluster mode: the depthwise warps have finished (and proxy-fenced) an operand tile -> broadcast thread
     uint32_t tmem_base;
     uint32_t pad;
 };
@@ -135,8 +148,11 @@ __device__ __forceinline__ ItemCoord decode_item(const TcParams& p, int w, int N
 
 // HALFK: the block has at most 32 input channels (conv1): the 16 channel pairs fill half a warp, so the two half-warps split the
 // warp's 4x4 pixel block into its upper and lower two rows instead of computing 32 zero channels each.
-template <typename T, int KS, int STRIDE, int NI, int TH, int TW, bool RELU6, bool HALFK = false>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// CLM: cluster mode.  1 = the CTAs of a cluster share one TILE and split its depthwise half and its output channels (TcParams::cs);
+// 2 = the CTAs of a cluster work on DIFFERENT tiles with the SAME output-channel split and share the weight stream: every CTA loads
+// 1/wmc of each weight block and TMA-multicasts it to all (TcParams::wmc).
+template <typename T, int KS, int STRIDE, int NI, int TH, int TW, bool RELU6, bool HALFK = false, int CLM = 0>
+__global__ void __launch_bounds__(CLM == 1 ? TC_THREADS_CL : TC_THREADS, 1)
 block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w,
                 const __grid_constant__ CUtensorMap tm_o0, const __grid_constant__ CUtensorMap tm_o1,
                 const __grid_constant__ CUtensorMap tm_o2, const __grid_constant__ CUtensorMap tm_o3, const TcParams p) {
@@ -162,11 +178,33 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
     uint32_t* s_head_w2 = reinterpret_cast<uint32_t*>(s_pw_affine + p.cpad_all);   // head weights of a channel pair, 16-bit x 2
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // role id of the sixteen worker warps: normally epilogue = warps 0..7, depthwise = 8..15; with TcParams::epi_high the two
+    // groups trade places (the warp schedulers favour one end of the id range, see TcParams::epi_high)
+    const int rwarp = (p.epi_high && warp < TC_DW_WARPS + TC_EPI_WARPS) ? (warp ^ 8) : warp;
+    constexpr bool CL = CLM == 1, CW = CLM == 2;
+    static_assert(!(HALFK && CLM != 0), "the half-K block has one K-block and resident weights: nothing to share");
+    const uint32_t cs = CL ? (uint32_t)p.cs : 1u;                      // tile-sharing cluster: size and this CTA's rank in it
+    const uint32_t crank = (CL || CW) ? cluster_ctarank() : 0u;
+    // Item walk.  Normally CTA b takes items b, b + grid, ...; in weight-multicast mode the UNIT is a cluster-item = wmc
+    // consecutive tiles x one output-channel split (every CTA of the cluster then streams the same weights in the same order):
+    // cluster c takes units c, c + n_clusters, ... and rank r of it the unit's tile r.
+    const uint32_t wmc = CW ? (uint32_t)p.wmc : 1u;
+    const int u_first = CW ? (int)(blockIdx.x / wmc) : (int)blockIdx.x;
+    const int u_stride = CW ? (int)(gridDim.x / wmc) : (int)gridDim.x;
+    const int u_count = CW ? p.items / (int)wmc : p.items;             // tiles % wmc == 0 (checked by the host)
+    auto item_of = [&](int u) -> int {
+        if (!CW) return u;
+        const int g = (int)fdiv40((uint32_t)u, p.mg_splits), sp = u - g * p.splits;
+        return (g * (int)wmc + (int)crank) * p.splits + sp;
+    };
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < TC_MAX_IN; ++i) { mbar_init(smem_u32(&bars->in_full[i]), 1); mbar_init(smem_u32(&bars->in_empty[i]), TC_DW_WARPS); }
-        for (int i = 0; i < TC_MAX_A; ++i) { mbar_init(smem_u32(&bars->a_full[i]), TC_DW_WARPS); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
-        for (int i = 0; i < TC_MAX_B; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), 1); }
+        // cluster mode: an A stage is full after ONE arrival (the owner's broadcast thread, or this CTA's own expect_tx for a
+        // tile that arrives by bulk copy) and free again when the MMA streams of all cs CTAs have committed past it
+        for (int i = 0; i < TC_MAX_A; ++i) { mbar_init(smem_u32(&bars->a_full[i]), CL ? 1 : TC_DW_WARPS); mbar_init(smem_u32(&bars->a_empty[i]), (CL && (p.cl_debug & 1)) ? 1u : cs); }
+        for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars->dw_done[i]), TC_DW_WARPS);
+        for (int i = 0; i < TC_MAX_B; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), wmc); }   // multicast: freed by all
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), (p.epi_colsplit || p.epi_wide) ? TC_EPI_WARPS : TC_EPI_WARPS / 2); }
         fence_barrier_init();
     }
@@ -176,21 +214,22 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         tma_prefetch_desc(&tm_w);
         if (p.epi_tma) { tma_prefetch_desc(&tm_o0); if (p.upsample) { tma_prefetch_desc(&tm_o1); tma_prefetch_desc(&tm_o2); tma_prefetch_desc(&tm_o3); } }
     }
-    for (int i = threadIdx.x; i < p.cpad_all; i += TC_THREADS) {          // pointwise BN affine (+ head weights) -> smem
+    for (int i = threadIdx.x; i < p.cpad_all; i += (int)blockDim.x) {      // pointwise BN affine (+ head weights) -> smem
         s_pw_affine[i] = p.pw_affine[i];
         if (p.head && !(i & 1)) s_head_w2[i >> 1] = MF::pack(p.head_w[i], p.head_w[i + 1]);   // cpad_all is even
     }
     if constexpr (HALFK) {
         // channels 32..63 of every A row are never written by the depthwise warps: zero the stages once (their products meet
         // the zero-filled K rows of the weights, but 0 x NaN from uninitialised shared memory would still poison the sum)
-        for (int i = threadIdx.x; i < p.s_a * (TC_A_STAGE_BYTES / 16); i += TC_THREADS)
+        for (int i = threadIdx.x; i < p.s_a * (TC_A_STAGE_BYTES / 16); i += (int)blockDim.x)
             reinterpret_cast<uint4*>(smem + a_off)[i] = make_uint4(0u, 0u, 0u, 0u);
         fence_proxy_async();
     }
     pdl_launch_dependents();                       // the next kernel may begin its own prologue
     pdl_wait_prior_grid();                         // everything below reads what the previous kernel wrote
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CLM != 0) cluster_sync_all();    // every CTA's barriers exist before a peer may signal or copy into them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
@@ -201,9 +240,10 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         if (lane == 0) {
             Ring rin;
             int tr = 0;
-            for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
+            for (int u = u_first; u < u_count; u += u_stride) {
+                const int w = item_of(u);
                 const ItemCoord c = decode_item(p, w, NI, TH, TW);
-                for (int kb = 0; kb < p.kblocks; ++kb, rin.next((uint32_t)p.s_in)) {
+                for (int kb = CL ? (int)crank : 0; kb < p.kblocks; kb += (int)cs, rin.next((uint32_t)p.s_in)) {     // cluster mode: my K-blocks only
                     const uint32_t s = rin.s, ph = rin.ph;
                     mbar_wait_sleep(smem_u32(&bars->in_empty[s]), ph ^ 1u, (uint32_t)p.sleep_ns >> 2);
                     mbar_expect_tx(smem_u32(&bars->in_full[s]), (uint32_t)(p.in_stage_bytes + p.dwp_bytes));
@@ -218,8 +258,11 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         } else if (lane == 1) {
             Ring rb;
             bool first = true;
-            for (int w = blockIdx.x; w < p.items; w += gridDim.x, first = false) {
+            const uint16_t w_mask = (uint16_t)((1u << wmc) - 1u);
+            const uint32_t slice_rows = (uint32_t)p.bn / wmc, slice_bytes = slice_rows * 128u;   // this CTA's share of a weight block
+            for (int u = u_first; u < u_count; u += u_stride, first = false) {
                 if (p.b_resident && !first) break;
+                const int w = item_of(u);
                 const int n0 = (w - (int)fdiv40((uint32_t)w, p.mg_splits) * p.splits) * p.n_cta;
                 for (int kb = 0; kb < p.kblocks; ++kb)
                     for (int nbi = 0; nbi < p.nb; ++nbi) {
@@ -232,8 +275,12 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                             rb.next((uint32_t)p.s_b);
                         }
                         mbar_expect_tx(smem_u32(&bars->b_full[sb]), (uint32_t)p.b_stage_bytes);
-                        tma_load_2d(smem_base + b_off + sb * p.b_stage_bytes, &tm_w, smem_u32(&bars->b_full[sb]), kb * TC_KBLK,
-                                    n0 + nbi * p.bn);
+                        if constexpr (CW)      // rows [crank * bn / wmc, ...) of the block, delivered to the same stage of every CTA
+                            tma_load_2d_multicast(smem_base + b_off + sb * p.b_stage_bytes + crank * slice_bytes, &tm_w,
+                                                  smem_u32(&bars->b_full[sb]), kb * TC_KBLK, n0 + nbi * p.bn + (int)(crank * slice_rows), w_mask);
+                        else
+                            tma_load_2d(smem_base + b_off + sb * p.b_stage_bytes, &tm_w, smem_u32(&bars->b_full[sb]), kb * TC_KBLK,
+                                        n0 + nbi * p.bn);
                     }
             }
         }
@@ -253,11 +300,32 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
             Ring ra, rb, racc;
             int tr = 0;
             bool first = true;
-            for (int w = blockIdx.x; w < p.items; w += gridDim.x, racc.next((uint32_t)p.nacc), first = false) {
+            // cluster mode: operand tiles of K-blocks another CTA owns arrive by bulk copy; this thread arms a stage's barrier with
+            // the expected bytes for its NEXT use as soon as the current use has been observed complete (kb_arm = K-block of that
+            // next use, q_left = K-block uses of this CTA's whole run that are not armed yet)
+            int kb_arm = 0;
+            long q_left = 0;
+            const uint16_t cl_mask = (uint16_t)((1u << cs) - 1u), cl_mask_w = (uint16_t)((1u << wmc) - 1u);
+            if constexpr (CL) {
+                const int n_it = u_first < u_count ? (u_count - 1 - u_first) / u_stride + 1 : 0;
+                q_left = (long)n_it * p.kblocks;
+                for (int s = 0; s < p.s_a && q_left > 0; ++s, --q_left) {
+                    if ((uint32_t)kb_arm % cs != crank) mbar_expect_tx(bar_a_full + 8u * (uint32_t)s, (uint32_t)TC_A_STAGE_BYTES);
+                    if (++kb_arm == p.kblocks) kb_arm = 0;
+                }
+            }
+            for (int u = u_first; u < u_count; u += u_stride, racc.next((uint32_t)p.nacc), first = false) {
                 mbar_wait_sleep(bar_acc_empty + 8u * racc.s, racc.ph ^ 1u, (uint32_t)p.mma_sleep_ns);   // epilogue has drained this accumulator
                 const uint32_t d_tmem = tmem_base + racc.s * (uint32_t)p.n_cta;
                 for (int kb = 0; kb < p.kblocks; ++kb, ra.next((uint32_t)p.s_a)) {
                     mbar_wait_sleep(bar_a_full + 8u * ra.s, ra.ph, (uint32_t)p.mma_sleep_ns);
+                    if constexpr (CL) {
+                        if (q_left > 0) {
+                            if ((uint32_t)kb_arm % cs != crank) mbar_expect_tx(bar_a_full + 8u * ra.s, (uint32_t)TC_A_STAGE_BYTES);
+                            if (++kb_arm == p.kblocks) kb_arm = 0;
+                            --q_left;
+                        }
+                    }
                     tc_fence_after();
                     TC_TRACE(4, tr);
                     const uint32_t a_lo = a_lo0 + ra.s * a_step;
@@ -279,27 +347,60 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                         umma_f16_lohi(dcol, a_lo + 2, b_lo + 2, kSw128DescHi, idesc, 1u);     // +32 B (16 elements) per K step
                         umma_f16_lohi(dcol, a_lo + 4, b_lo + 4, kSw128DescHi, idesc, 1u);
                         umma_f16_lohi(dcol, a_lo + 6, b_lo + 6, kSw128DescHi, idesc, 1u);
-                        if (!p.b_resident) umma_commit(bar_b_empty + 8u * sb);
+                        if (!p.b_resident) {
+                            if constexpr (CW) umma_commit_multicast(bar_b_empty + 8u * sb, cl_mask_w);   // the stage is refilled for all CTAs at once
+                            else umma_commit(bar_b_empty + 8u * sb);
+                        }
                     }
-                    umma_commit(bar_a_empty + 8u * ra.s);
+                    if (CL && !(p.cl_debug & 1)) umma_commit_multicast(bar_a_empty + 8u * ra.s, cl_mask);    // frees the stage in every CTA's count
+                    else umma_commit(bar_a_empty + 8u * ra.s);
                     TC_TRACE(5, tr); ++tr;
                 }
                 umma_commit(bar_acc_full + 8u * racc.s);
             }
         }
-    } else if (warp >= TC_WARP_DW0 && warp < TC_WARP_DW0 + TC_DW_WARPS) {
+    } else if (CL && warp == TC_WARP_BCAST) {
+        // =========================== cluster mode: broadcast thread ===========================
+        // An operand tile the local depthwise warps have finished goes to the same A stage of every other CTA of the cluster as
+        // one 16 KB bulk copy each (async proxy at both ends, completion bytes on the receiver's a_full).  A warp of its own: a
+        // lane of the TMA warp parked in a barrier wait does not reliably let its sibling lanes run.
+        if (lane == 0) {
+            Ring ra;
+            uint32_t o = 0;
+            for (int u = u_first; u < u_count; u += u_stride)
+                for (int kb = 0; kb < p.kblocks; ++kb, ra.next((uint32_t)p.s_a)) {
+                    if ((uint32_t)kb % cs != crank) continue;
+                    mbar_wait(smem_u32(&bars->dw_done[o & 3u]), (o >> 2) & 1u);
+                    ++o;
+                    const uint32_t slot = smem_base + a_off + ra.s * TC_A_STAGE_BYTES, bar = smem_u32(&bars->a_full[ra.s]);
+                    mbar_arrive(bar);                                            // the local MMA stream reads it in place
+                    for (uint32_t peer = 0; peer < cs; ++peer)
+                        if (peer != crank) bulk_copy_to_peer(mapa_u32(slot, peer), slot, (uint32_t)TC_A_STAGE_BYTES, mapa_u32(bar, peer));
+                }
+        }
+    } else if (rwarp >= TC_WARP_DW0 && rwarp < TC_WARP_DW0 + TC_DW_WARPS) {
         // =========================== depthwise workers ===========================
         constexpr int BPR = TW / 4, BPI = (TH / 4) * BPR;
-        const int dwi = warp - TC_WARP_DW0;
+        const int dwi = rwarp - TC_WARP_DW0;
         const int ni = dwi / BPI, rem = dwi % BPI;
         const int br = rem / BPR, bc = rem % BPR;
         const uint32_t in_warp_off = (uint32_t)((ni * IH + br * 4 * STRIDE) * IW + bc * 4 * STRIDE) * 128u + lane * 4u;
         Ring rin, ra;
         int tr = 0;
+        uint32_t own = 0;                                  // cluster mode: operand tiles this CTA has produced
         const bool tracer = dwi == 0 && lane == 0;
-        for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
-            for (int kb = 0; kb < p.kblocks; ++kb, rin.next((uint32_t)p.s_in), ra.next((uint32_t)p.s_a)) {
+        for (int u = u_first; u < u_count; u += u_stride) {
+            for (int kb = 0; kb < p.kblocks; ++kb, ra.next((uint32_t)p.s_a)) {
+                if (CL && (uint32_t)kb % cs != crank) {
+                    // A peer computes this K-block; its tile arrives by bulk copy.  The stage's release is still awaited, in order:
+                    // a parity wait only tells "one phase further", and this CTA's next own use of a stage may lie several uses
+                    // ahead (the uses in between belong to peers) -- skipping them would let the parity alias.  Free of charge:
+                    // uses are released in K-block order, so an earlier one never completes later than the one needed next.
+                    mbar_wait(smem_u32(&bars->a_empty[ra.s]), ra.ph ^ 1u);
+                    continue;
+                }
                 const uint32_t s = rin.s, ph = rin.ph, sa = ra.s, pha = ra.ph;
+                rin.next((uint32_t)p.s_in);
                 mbar_wait_sleep(smem_u32(&bars->in_full[s]), ph, (uint32_t)p.dw_sleep_ns);
                 if (tracer) TC_TRACE(1, tr);
                 const uint8_t* stage = smem + in_off + s * p.in_stage_stride;
@@ -439,9 +540,10 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                 // the input stage can be refilled as soon as every warp has read it
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bars->in_empty[s]));
-                fence_proxy_async();             // generic-proxy writes -> visible to the tensor core (async proxy)
+                fence_proxy_async();             // generic-proxy writes -> visible to the tensor core / the bulk copies (async proxy)
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bars->a_full[sa]));
+                if (lane == 0) mbar_arrive(CL ? smem_u32(&bars->dw_done[own & 3u]) : smem_u32(&bars->a_full[sa]));
+                ++own;
                 if (tracer) { TC_TRACE(3, tr); ++tr; }
             }
         }
@@ -449,7 +551,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         // =========================== epilogue warps ===========================
         // Two independent groups of four warps; group g drains TMEM accumulator g, i.e. every second item, so one
         // group's TMEM-load / barrier latency overlaps the other group's math and stores.
-        const int ew = warp - TC_WARP_EPI0;
+        const int ew = rwarp - TC_WARP_EPI0;               // (rwarp and warp agree modulo 4: the TMEM lane quarter is the hardware's)
         const int q = ew & 3, grp = ew >> 2;               // TMEM lane quarter (== warp % 4), group / accumulator index
         const int m = q * 32 + lane;                       // accumulator row == pixel of the tile
         const int e_ni = m / (TH * TW), e_ty = (m / TW) % TH, e_tx = m % TW;
@@ -466,8 +568,9 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         uint32_t ab = (ngrp == 2 && !cs) ? (uint32_t)grp : 0u, pa = 0;   // accumulator buffer and its mbarrier phase
         int tr = 0;
         uint32_t stg_flip = 0;
-        const int w_step = (cs ? 1 : ngrp) * (int)gridDim.x;
-        for (int w = blockIdx.x + ((cs || wide) ? 0 : grp) * gridDim.x; (grp < ngrp || wide) && w < p.items; w += w_step) {
+        const int u_step = (cs ? 1 : ngrp) * u_stride;
+        for (int u = u_first + ((cs || wide) ? 0 : grp) * u_stride; (grp < ngrp || wide) && u < u_count; u += u_step) {
+            const int w = item_of(u);
             const ItemCoord c = decode_item(p, w, NI, TH, TW);
             const int img = c.img0 + e_ni, oy = c.oy0 + e_ty, ox = c.ox0 + e_tx;
             const bool valid = img < p.n && oy < p.h_out && ox < p.w_out;
@@ -645,7 +748,8 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CLM != 0) cluster_sync_all();    // nobody leaves while a peer may still copy into / signal this CTA
+    else __syncthreads();
     if (warp == TC_WARP_MMA) {
         tc_fence_after();
         tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -673,6 +777,8 @@ struct BlockTcPlan {
     size_t smem_bytes;
     int dtype, ks, stride, tile;           // tile: 0 = (1,8,16), 1 = (2,8,8)
     int halfk = 0;                         // 1: c_in <= 32, the HALFK instance of the 3x3 stride-1 kernel
+    int tiles = 0;                         // 128-pixel tiles of the block (items / splits)
+    bool grid_final = false;               // cluster mode: the grid is sized by the occupancy query at the first launch
     TcLaunchOpts opts;                     // the plan's launch options at the time this block was prepared
     void* dwp = nullptr;                   // owned device copies (packed / padded)
     float2* pw_affine = nullptr;
@@ -685,6 +791,8 @@ static void plan_env_knobs(BlockPlanIn& q) {
     const char* a = getenv("FD_TC_MAX_NCTA");
     const char* b = getenv("FD_TC_NO_COLSPLIT");
     const char* c = getenv("FD_TC_NO_WIDE");
+    const char* d = getenv("FD_TC_CLUSTER");          // 1 = never, 2 / 4 = force that cluster size where the block admits it
+    if (d && *d) q.cluster = atoi(d);
     q.no_wide = (c && *c == '1') ? 1 : 0;
     q.max_n_cta = a ? atoi(a) : 0;
     q.no_colsplit = (b && *b == '1') ? 1 : 0;
@@ -703,9 +811,12 @@ bool block_tc_supported(int dtype, const StageGeom& g, bool head_fused) {
     return get_encode() != nullptr;
 }
 
-template <typename T, int KS, int STRIDE, int NI, int TH, int TW, bool RELU6, bool HALFK = false>
+template <typename T, int KS, int STRIDE, int NI, int TH, int TW, bool RELU6, bool HALFK = false, int CLM = 0>
 static int launch_inst2(BlockTcPlan* bp, cudaStream_t st) {
-    auto kern = block_tc_kernel<T, KS, STRIDE, NI, TH, TW, RELU6, HALFK>;
+    auto kern = block_tc_kernel<T, KS, STRIDE, NI, TH, TW, RELU6, HALFK, CLM>;
+    constexpr bool CL = CLM != 0;                      // launched on clusters (either mode)
+    const int csize = CLM == 1 ? bp->p.cs : bp->p.wmc; // CTAs per cluster
+    const int units = CLM == 1 ? bp->tiles : bp->p.items / (bp->p.wmc > 0 ? bp->p.wmc : 1);   // what a cluster walks
     static PerDeviceOnce attr_set;             // the opt-in is per device (and per kernel instance)
     int dev = -1;
     FD_CUDA_OK(cudaGetDevice(&dev));
@@ -714,17 +825,47 @@ static int launch_inst2(BlockTcPlan* bp, cudaStream_t st) {
         attr_set.done(dev);
     }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = bp->grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = bp->smem_bytes; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = bp->opts.pdl ? 1 : 0;
+    cfg.gridDim = bp->grid; cfg.blockDim = dim3(CLM == 1 ? TC_THREADS_CL : TC_THREADS); cfg.dynamicSmemBytes = bp->smem_bytes; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (CL) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = (unsigned)csize; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (CL && !bp->grid_final) {
+        // one CTA per SM and whole clusters per GPC: ask the runtime how many clusters of this shape are resident at once and
+        // let that many walk the tiles (a larger grid would still be correct -- clusters are independent -- only slower)
+        cfg.attrs = attr; cfg.numAttrs = (unsigned)na;
+        cfg.gridDim = dim3((unsigned)(units * csize), 1, 1);
+        int n_cl = 0;
+        FD_CUDA_OK(cudaOccupancyMaxActiveClusters(&n_cl, kern, &cfg));
+        if (n_cl < 1) return fail(FD_ERR_UNSUPPORTED, "cluster-mode block kernel: no cluster of this shape fits the device");
+        if (n_cl > units) n_cl = units;
+        bp->grid = dim3((unsigned)(n_cl * csize), 1, 1);
+        bp->grid_final = true;
+        cfg.gridDim = bp->grid;
+    }
+    if (bp->opts.pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = (unsigned)na;
     FD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, bp->tm_in, bp->tm_w, bp->tm_o[0], bp->tm_o[1], bp->tm_o[2], bp->tm_o[3], bp->p));
     FD_CUDA_OK(cudaGetLastError());
     return FD_OK;
 }
 template <typename T, int KS, int STRIDE, int NI, int TH, int TW, bool HALFK = false>
 static int launch_inst(BlockTcPlan* bp, cudaStream_t st) {
+    if constexpr (!HALFK) {
+        if (bp->p.cs > 1)
+            return bp->p.act == FD_ACT_RELU6 ? launch_inst2<T, KS, STRIDE, NI, TH, TW, true, false, 1>(bp, st)
+                                             : launch_inst2<T, KS, STRIDE, NI, TH, TW, false, false, 1>(bp, st);
+        if (bp->p.wmc > 1)
+            return bp->p.act == FD_ACT_RELU6 ? launch_inst2<T, KS, STRIDE, NI, TH, TW, true, false, 2>(bp, st)
+                                             : launch_inst2<T, KS, STRIDE, NI, TH, TW, false, false, 2>(bp, st);
+    }
     return bp->p.act == FD_ACT_RELU6 ? launch_inst2<T, KS, STRIDE, NI, TH, TW, true, HALFK>(bp, st)
                                      : launch_inst2<T, KS, STRIDE, NI, TH, TW, false, HALFK>(bp, st);
 }
@@ -762,6 +903,7 @@ BlockPlanOut block_tc_debug_plan(int ksize, int stride, int h_out, int w_out, in
     const int NI = q.tile ? 2 : 1, TW = q.tile ? 8 : 16;
     q.n_tiles = ((w_out + TW - 1) / TW) * ((h_out + 7) / 8) * ((n + NI - 1) / NI);
     q.barrier_bytes = (int)sizeof(TcBarriers); q.n_sms = 148;
+    q.cluster = 0;
     plan_env_knobs(q);
     return plan_block(q);
 }
@@ -824,6 +966,12 @@ static int padded_copy(const float* src, int n_src, int n_dst, float** out) {
     return FD_OK;
 }
 
+// Default choice of the weight-multicast cluster size for a block (1 = none); FD_TC_WMC overrides.
+static int block_wmc_auto(const StageGeom& g, const BlockPlanOut& po, int n_tiles) {
+    (void)g; (void)po; (void)n_tiles;
+    return 1;
+}
+
 int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float head_scale, float head_bias, int head_act,
                      void* head_out, bool tma_epilogue, const TcLaunchOpts& opts, BlockTcPlan** out) {
     PFN_encodeTiled encode = get_encode();
@@ -855,7 +1003,9 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
     BlockPlanIn pin{};
     pin.ksize = g.ksize; pin.stride = g.stride; pin.tile = bp->tile; pin.c_in = g.c_in; pin.c_out = g.c_out; pin.n_tiles = n_tiles;
     pin.head = p.head; pin.barrier_bytes = (int)sizeof(TcBarriers); pin.n_sms = opts.n_sms;
+    pin.cluster = (opts.cluster && !bp->halfk) ? 0 : 1;
     plan_env_knobs(pin);
+    if (bp->halfk) pin.cluster = 1;
     const BlockPlanOut po = plan_block(pin);
     if (!po.ok) { delete bp; return fail(FD_ERR_UNSUPPORTED, "fused block does not fit shared memory"); }
     const int splits = po.splits;
@@ -864,6 +1014,21 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
     p.in_stage_bytes = po.in_stage_bytes; p.dwp_bytes = po.dwp_bytes; p.in_stage_stride = po.in_stage_stride; p.cpad_all = po.cpad_all;
     p.s_a = po.s_a; p.n_stg = po.n_stg; p.epi_groups = po.epi_groups; p.s_in = po.s_in; p.s_b = po.s_b; p.bn = po.bn; p.nb = po.nb;
     p.b_resident = po.b_resident; p.b_stage_bytes = po.b_stage_bytes;
+    p.cs = po.cs; bp->tiles = n_tiles;
+    // Weight-multicast clusters (mode 2): wmc consecutive tiles with the same output-channel split stream ONE copy of the weights
+    // out of the L2 -- the small-map blocks move 110-125 MB through the L2 -> SM fabric per launch, more than half of it the same
+    // weight blocks fetched again by every CTA (ncu l1tex__m_xbar2l1tex_read_bytes, profiles/r02_v1_kernels.csv).
+    { const char* e = getenv("FD_TC_EPI_HIGH"); p.epi_high = (e && *e) ? atoi(e) : 0; }
+    p.wmc = 1;
+    {
+        const char* e = getenv("FD_TC_WMC");               // 1 = never, 2 / 4 = force where the block admits it
+        int want = e && *e ? atoi(e) : 0;
+        if (!opts.cluster || bp->halfk) want = 1;
+        if (want == 0) want = block_wmc_auto(g, po, n_tiles);
+        while (want > 1 && !(p.cs == 1 && !p.b_resident && n_tiles % want == 0 && p.bn % (8 * want) == 0 && n_tiles / want >= 1)) want >>= 1;
+        p.wmc = want < 1 ? 1 : want;
+    }
+    { const char* e = getenv("FD_TC_CL_DEBUG"); p.cl_debug = e ? atoi(e) : 0; }        // bring-up switches of the cluster mode
     bp->smem_bytes = (size_t)po.smem_bytes;
     const int taps = g.ksize * g.ksize;
     (void)splits;
@@ -875,6 +1040,13 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
         p.dw_sleep_ns = b ? atoi(b) : 0;
     }
     bp->grid = dim3((unsigned)(p.items < sms ? p.items : sms), 1, 1);
+    if (p.cs > 1) {                                   // whole clusters; refined by the occupancy query at the first launch
+        int n_cl = sms / p.cs; if (n_cl > n_tiles) n_cl = n_tiles; if (n_cl < 1) n_cl = 1;
+        bp->grid = dim3((unsigned)(n_cl * p.cs), 1, 1);
+    } else if (p.wmc > 1) {
+        int n_cl = sms / p.wmc; if (n_cl > p.items / p.wmc) n_cl = p.items / p.wmc; if (n_cl < 1) n_cl = 1;
+        bp->grid = dim3((unsigned)(n_cl * p.wmc), 1, 1);
+    }
 
     // packed / padded parameter copies (device -> device)
     int rc = FD_OK;
@@ -913,7 +1085,7 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
     {   // pointwise weights [c_out][c_in] viewed as (K = c_in, N = c_out); box (64, bn); 128B swizzle
         cuuint64_t dims[2] = {(cuuint64_t)g.c_in, (cuuint64_t)g.c_out};
         cuuint64_t strides[1] = {(cuuint64_t)g.c_in * es};
-        cuuint32_t box[2] = {(cuuint32_t)TC_KBLK, (cuuint32_t)p.bn};
+        cuuint32_t box[2] = {(cuuint32_t)TC_KBLK, (cuuint32_t)(p.bn / p.wmc)};      // multicast mode: each CTA loads its share of a block
         cuuint32_t estr[2] = {1, 1};
         CUresult r = encode(&bp->tm_w, dt, 2, const_cast<void*>(a.pw_w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -939,7 +1111,10 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
         }
     }
     char buf[160];
-    snprintf(buf, sizeof(buf), "block_tc<k%d,s%d,%s%s>%s%s%s[n%dx%d,bn%d%s,kb%d,in%d,a%d,b%d,e%dx%d%s]", g.ksize, g.stride, bp->tile ? "2x8x8" : "1x8x16", bp->halfk ? ",k32" : "",
+    char clbuf[16] = "";
+    if (p.cs > 1) snprintf(clbuf, sizeof(clbuf), ",cl%d", p.cs);
+    else if (p.wmc > 1) snprintf(clbuf, sizeof(clbuf), ",wmc%d", p.wmc);
+    snprintf(buf, sizeof(buf), "block_tc<k%d,s%d,%s%s%s>%s%s%s[n%dx%d,bn%d%s,kb%d,in%d,a%d,b%d,e%dx%d%s]", g.ksize, g.stride, bp->tile ? "2x8x8" : "1x8x16", bp->halfk ? ",k32" : "", clbuf,
              g.upsample ? "+up2x" : "", a.skip ? (p.epi_red ? "+skip(red)" : "+skip") : "", p.head ? "+head" : (p.epi_tma ? "+tmast" : ""), p.n_cta, p.splits, p.bn,
              p.b_resident ? "r" : "", p.kblocks, p.s_in, p.s_a, p.s_b, p.epi_groups, p.head ? 0 : p.n_stg / p.epi_groups, p.epi_colsplit ? "c" : (p.epi_wide ? "w" : ""));
     bp->name = buf;

@@ -58,7 +58,7 @@ struct ChainBarriers {
     uint64_t dwp_full[CH_SD], dwp_empty[CH_SD];
     uint64_t aff_full[2], aff_empty[2];
     uint64_t acc_full;                  // tcgen05.commit multicast: all MMAs of the layer done
-    uint64_t halo_full;                 // 16 remote arrivals: the peer has written my halo row of the next layer
+    uint64_t halo_full;                 // one remote arrival (cluster-scope release): the peer has written my halo row of the next layer
     uint64_t act_free;                  // the last layer's output has left the activation blocks (TMA stores have read them)
     uint32_t tmem_base, pad;
 };
@@ -95,30 +95,7 @@ struct ChainMaps {
                                        // SWIZZLE_128B; column 14 and channels >= c_out are clipped by the hardware
 };
 
-// ---- cluster / 2-CTA PTX -------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
-    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// wait on a LOCAL barrier whose arrivals come (also) from the peer CTA: acquire at cluster scope
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, uint32_t ns) {
-    for (;;) {
-        uint32_t ok;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (ok) break;
-        if (ns) __nanosleep(ns);
-    }
-}
-__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint4 v) {
-    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
+// ---- 2-CTA PTX (cluster helpers: fd_tc_common.cuh) -------------------------------------------------------
 // TMA tile load issued by either CTA of the pair, completion bytes posted on the LEADER's mbarrier
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -167,7 +144,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
         for (int i = 0; i < CH_SD; ++i) { mbar_init(smem_u32(&bars->dwp_full[i]), 1); mbar_init(smem_u32(&bars->dwp_empty[i]), CH_WORKERS / 2); }
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->aff_full[i]), 1); mbar_init(smem_u32(&bars->aff_empty[i]), CH_WORKERS); }
         mbar_init(smem_u32(&bars->acc_full), 1);
-        mbar_init(smem_u32(&bars->halo_full), CH_WORKERS);
+        mbar_init(smem_u32(&bars->halo_full), 1);
         mbar_init(smem_u32(&bars->act_free), 1);
         fence_barrier_init();
     }
@@ -249,14 +226,14 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                 for (int l = 0; l < p.n_layers; ++l) {
                     const ChainLayer& L = p.L[l];
                     for (int kb = 0; kb < L.kblocks; ++kb) {
-                        mbar_wait_cluster(smem_u32(&bars->a_full[kb]), (a_par >> kb) & 1u, 0u);
+                        mbar_wait(smem_u32(&bars->a_full[kb]), (a_par >> kb) & 1u);      // CTA-scope acquire: a cluster-scope one costs a CCTL.IVALL per probe
                         a_par ^= 1u << kb;
                         tc_fence_after();
                         if (kb == 0 && img == cluster_id) CH_TRACE(7, l);
                         const uint32_t a_lo = a_lo0 + (uint32_t)kb * (CH_BLK >> 4);
                         for (int nh = 0; nh < L.nh; ++nh, ++seq) {
                             const uint32_t s = seq & (CH_SB - 1), ph = (seq / CH_SB) & 1u;
-                            mbar_wait_cluster(smem_u32(&bars->b_full[s]), ph, 0u);
+                            mbar_wait(smem_u32(&bars->b_full[s]), ph);
                             tc_fence_after();
                             if (kb == 0 && nh == 0 && img == cluster_id) CH_TRACE(11, l);
                             const int n_ins = min(256, L.n_pad - nh * 256);
@@ -325,6 +302,45 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                     const f32x2 bi = *reinterpret_cast<const f32x2*>(prm + 9 * 128 + 256 + lane * 8);
                     const uint8_t* in0 = blk + s0 * 128;
                     uint32_t o[7][2];
+#ifdef FD_CHAIN_DW_FHFMA       // build-time A/B: measured 83.5 us against 79.1 us for the FFMA2 form below (the MMA stream, which shares
+                              // the schedulers with the workers, finishes later under the denser FHFMA stream)
+                    // 16-bit x 16-bit + fp32 on FHFMA (0.84 / clk / scheduler, no widening): with four worker warps per scheduler
+                    // the FMA pipe is the limit, where 252 FHFMA beat 126 FFMA2 + 90 HADD2.F32 (both pairs of two-cycle
+                    // instructions); bit-identical either way (exact products, same accumulation order)
+                    if (dw_active) {
+                        uint32_t wv[9];
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) wv[i] = *reinterpret_cast<const uint32_t*>(prm + i * 128 + lane * 4);
+                        float acc[7][2][2];
+#pragma unroll
+                        for (int a = 0; a < 7; ++a)
+#pragma unroll
+                            for (int b = 0; b < 2; ++b) acc[a][b][0] = acc[a][b][1] = 0.f;
+#pragma unroll
+                        for (int iy = 0; iy < 9; ++iy) {
+                            uint32_t row[4];
+#pragma unroll
+                            for (int ix = 0; ix < 4; ++ix) {
+                                const int k = iy * CH_PITCH + ix;
+                                row[ix] = *reinterpret_cast<const uint32_t*>(in0 + k * 128 + rd_off[k & 7]);
+                            }
+#pragma unroll
+                            for (int oy = 0; oy < 7; ++oy) {
+                                const int ky = iy - oy;
+                                if (ky < 0 || ky >= 3) continue;
+#pragma unroll
+                                for (int ox = 0; ox < 2; ++ox)
+#pragma unroll
+                                    for (int kx = 0; kx < 3; ++kx) MF::fma2(acc[oy][ox][0], acc[oy][ox][1], row[ox + kx], wv[ky * 3 + kx]);
+                            }
+                        }
+#pragma unroll
+                        for (int oy = 0; oy < 7; ++oy)
+#pragma unroll
+                            for (int ox = 0; ox < 2; ++ox)
+                                o[oy][ox] = MF::template pack_act<RELU6>(ffma2_abc(f32x2_make(acc[oy][ox][0], acc[oy][ox][1]), sc, bi));
+                    }
+#else
                     if (dw_active) {
                         f32x2 acc[7][2];
 #pragma unroll
@@ -357,6 +373,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
 #pragma unroll
                             for (int ox = 0; ox < 2; ++ox) o[oy][ox] = MF::template pack_act<RELU6>(ffma2_abc(acc[oy][ox], sc, bi));
                     }
+#endif
                     __syncwarp();
                     if (tr0 && kb == 0) CH_TRACE(1, l);
                     if (lane == 0) mbar_arrive(smem_u32(&bars->dwp_empty[ds]));
@@ -371,7 +388,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                     }
                     fence_proxy_async();                       // generic-proxy writes -> visible to the tensor cores (async proxy)
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(leader_a_full0 + 8u * (uint32_t)kb);
+                    if (lane == 0) mbar_arrive_remote_cta_scope(leader_a_full0 + 8u * (uint32_t)kb);
                 }
                 dseq_base += (uint32_t)L.kblocks;
                 if (tr0) CH_TRACE(2, l);
@@ -427,12 +444,12 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                 }
                 fence_proxy_async();        // these generic-proxy writes precede async-proxy accesses (MMA reads, the next image's TMA)
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(smem_u32(&bars->aff_empty[as]));
-                    if (!last) mbar_arrive_cluster(peer_halo_full);       // release.cluster: my halo stores are visible to the peer
-                }
-                // every local worker has left the epilogue (TMEM drained, activations written) ...
+                if (lane == 0) mbar_arrive(smem_u32(&bars->aff_empty[as]));
+                // every local worker has left the epilogue (TMEM drained, activations written, halo row stored into the peer) ...
                 asm volatile("bar.sync %0, %1;" ::"r"(3), "r"(CH_WORKERS * 32) : "memory");
+                // ... so ONE cluster-scope release (MEMBAR.GPU class, ~500 cycles) publishes all sixteen warps' halo stores: the
+                // barrier orders them before this thread, and a release is cumulative
+                if (!last && threadIdx.x == 0) mbar_arrive_cluster(peer_halo_full);
                 if (tr0) CH_TRACE(5, l);
                 // ... and the peer has delivered my halo row
                 if (!last) { mbar_wait_cluster(smem_u32(&bars->halo_full), halo_seq & 1u, 0u); ++halo_seq; }

@@ -125,6 +125,7 @@ struct TcLaunchOpts {
     int pdl = 1;             // programmatic dependent launch attribute on every launch
     int sleep_ns = 0;        // > 0: latency-tolerant mbarrier waits back off with nanosleep instead of spinning
     int n_sms = 148;         // SMs of the plan's device (grid size and the planner's wave model)
+    int cluster = 1;         // 1: the block planner may run small-map blocks on thread-block clusters that share the depthwise half
 };
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE property of a kernel: remember which devices have it.

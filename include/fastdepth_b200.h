@@ -109,6 +109,10 @@ int fd_plan_set_stage_weights(fd_plan* plan, int stage,
  *   "chain"      1 = a run of consecutive 3x3 stride-1 blocks on a small feature map (conv7..conv11 at 14x14) executes as ONE
  *                kernel on 2-CTA clusters with every intermediate activation resident in shared memory; the intermediate
  *                stages' buffers are then not written (set 0 for stage-by-stage inspection)  [default 1]
+ *   "cluster"    1 = the block planner may run a block on thread-block clusters of 2 or 4 CTAs that share one 128-pixel tile:
+ *                each CTA computes the depthwise half of a quarter (half) of the K-blocks, broadcasts its operand tiles to
+ *                the others through distributed shared memory and runs the MMAs of one output-channel split (chosen by
+ *                the planner's cost model for the small-map, many-channel blocks)  [default 1]
  *   "wait_sleep_ns" > 0: latency-tolerant roles of the fused block kernel (epilogue warps waiting for an
  *                accumulator, TMA producer waiting for a free stage) sleep this many ns between barrier
  *                probes instead of spinning (measured: no effect on B200, the spinning waiters do not
@@ -169,7 +173,8 @@ int fd_plan_trace_stage(fd_plan* plan, int stage, void* y_dev, void* stream,
 /* Debug (host only, needs no GPU): the shared-memory / pipeline plan the fused block kernel would use for one
  * block.  out[0..15] = {ok, splits, n_cta, items, kblocks, s_in, s_a, s_b, bn, nb, b_resident, epi_groups, n_stg,
  * smem_bytes, tmem_cols, in_stage_stride}; with cap >= 18 also out[16..17] = {nacc (TMEM accumulators), epi_colsplit},
- * with cap >= 19 out[18] = epi_wide.  cap must be at least 16. */
+ * with cap >= 19 out[18] = epi_wide, with cap >= 20 out[19] = cs (cluster size: CTAs sharing one tile's depthwise half).
+ * cap must be at least 16. */
 int fd_debug_block_plan(int ksize, int stride, int h_out, int w_out, int n, int c_in, int c_out, int head,
                         int* out, int cap);
 

@@ -8,14 +8,14 @@ import pytest
 from fastdepth_b200 import _lib, synthetic
 
 KEYS = ('ok', 'splits', 'n_cta', 'items', 'kblocks', 's_in', 's_a', 's_b', 'bn', 'nb', 'b_resident', 'epi_groups',
-        'n_stg', 'smem_bytes', 'tmem_cols', 'in_stage_stride', 'nacc', 'epi_colsplit', 'epi_wide')
+        'n_stg', 'smem_bytes', 'tmem_cols', 'in_stage_stride', 'nacc', 'epi_colsplit', 'epi_wide', 'cs')
 STRIDES = (2, 1, 2, 1, 2, 1, 2, 1, 1, 1, 1, 1, 2, 1)
 
 
 def plan(ks, stride, h, w, n, cin, cout, head=0):
     lib = _lib.load()
-    out = (ctypes.c_int * 19)()
-    _lib.check(lib.fd_debug_block_plan(ks, stride, h, w, n, cin, cout, head, out, 19))
+    out = (ctypes.c_int * 20)()
+    _lib.check(lib.fd_debug_block_plan(ks, stride, h, w, n, cin, cout, head, out, 20))
     return dict(zip(KEYS, out))
 
 
@@ -43,7 +43,8 @@ def test_every_block_gets_a_valid_plan(built_lib, widths, shape):
         assert p['nacc'] == 2 or (p['epi_colsplit'] == 1 and p['epi_groups'] == 2), (name, p)   # one accumulator: both groups drain it
         assert not p['epi_colsplit'] or (p['epi_groups'] == 2 and p['n_cta'] > 64 and not head), (name, p)
         assert p['n_cta'] * p['splits'] >= cout and (p['splits'] == 1 or p['n_cta'] % 64 == 0), (name, p)
-        assert p['s_in'] >= 1 and 2 <= p['s_a'] <= 4 and p['bn'] * p['nb'] >= p['n_cta'], (name, p)
+        assert p['s_in'] >= 1 and 2 <= p['s_a'] <= (6 if p['cs'] > 1 else 4) and p['bn'] * p['nb'] >= p['n_cta'], (name, p)
+        assert p['cs'] == 1 or (p['cs'] in (2, 4) and p['splits'] == p['cs'] and p['kblocks'] >= p['cs'] and p['nacc'] == 2 and not head), (name, p)
         assert p['bn'] >= min(64, p['n_cta']), (name, p)            # no narrow MMAs
         assert p['epi_groups'] in (1, 2) and (head or p['n_stg'] in (p['epi_groups'], 2 * p['epi_groups'])), (name, p)
         if p['b_resident']:
@@ -83,7 +84,10 @@ def test_planner_invariants_on_random_blocks(built_lib):
         assert p['nacc'] in (1, 2) and p['nacc'] * p['n_cta'] <= p['tmem_cols'] <= 512, ctx
         assert p['tmem_cols'] >= 32 and p['tmem_cols'] & (p['tmem_cols'] - 1) == 0, ctx
         assert p['bn'] % 16 == 0 and p['bn'] <= 256 and p['bn'] * p['nb'] >= p['n_cta'] > p['bn'] * (p['nb'] - 1), ctx
-        assert p['kblocks'] == (cin + 63) // 64 and 2 <= p['s_a'] <= 4 and 1 <= p['s_in'] <= 6, ctx
+        assert p['kblocks'] == (cin + 63) // 64 and 2 <= p['s_a'] <= (6 if p['cs'] > 1 else 4) and 1 <= p['s_in'] <= 6, ctx
+        # cluster mode: one split per CTA of the cluster, every CTA owns a K-block and a non-empty split, two accumulators
+        assert p['cs'] == 1 or (p['cs'] in (2, 4) and p['splits'] == p['cs'] and p['kblocks'] >= p['cs'] and p['nacc'] == 2 and
+                                p['n_cta'] * (p['cs'] - 1) < cout and not head), ctx
         assert p['s_in'] >= 2 or (p['kblocks'] == 1 and p['items'] <= 148), ctx
         assert 1 <= p['s_b'] <= 16 and (not p['b_resident'] or p['s_b'] == p['kblocks'] * p['nb']), ctx
         assert p['epi_groups'] in (1, 2), ctx

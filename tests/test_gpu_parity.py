@@ -311,10 +311,16 @@ def test_epilogue_organisations_and_item_shapes_agree_bitwise(widths, monkeypatc
     m, _ = make_model(widths, torch.float16, (224, 224))
     x = synthetic.synthetic_input(64, 224, 224, seed=11).cuda().half()     # the metric batch: only there does the planner
     outs, kernels = [], []                                                  # pick one 512-column accumulator per 14x14 tile
+    knobs = ('FD_TC_MAX_NCTA', 'FD_TC_NO_COLSPLIT', 'FD_TC_NO_WIDE', 'FD_TC_CLUSTER', 'FD_TC_WMC')
     for env, opts in (({}, {}),
-                      ({'FD_TC_MAX_NCTA': '256', 'FD_TC_NO_COLSPLIT': '1', 'FD_TC_NO_WIDE': '1'}, {}),
-                      ({'FD_TC_MAX_NCTA': '128'}, {'wait_sleep_ns': 200})):
-        for k in ('FD_TC_MAX_NCTA', 'FD_TC_NO_COLSPLIT', 'FD_TC_NO_WIDE'):
+                      ({'FD_TC_MAX_NCTA': '256', 'FD_TC_NO_COLSPLIT': '1', 'FD_TC_NO_WIDE': '1', 'FD_TC_CLUSTER': '1'}, {}),
+                      ({'FD_TC_MAX_NCTA': '128'}, {'wait_sleep_ns': 200}),
+                      ({'FD_TC_CLUSTER': '1'}, {}),                # never a cluster
+                      ({'FD_TC_CLUSTER': '2'}, {}),                # 2-CTA tile-sharing clusters wherever a block admits them
+                      ({'FD_TC_CLUSTER': '4'}, {}),                # 4-CTA ...
+                      ({'FD_TC_CLUSTER': '1', 'FD_TC_WMC': '2'}, {}),      # weight-multicast clusters of 2 tiles
+                      ({'FD_TC_CLUSTER': '1', 'FD_TC_WMC': '4'}, {})):     # ... of 4 tiles
+        for k in knobs:
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -330,11 +336,14 @@ def test_epilogue_organisations_and_item_shapes_agree_bitwise(widths, monkeypatc
     assert 'c]' in kernels[0] and 'w]' in kernels[0], kernels[0]    # default plan uses column-split and eight-warp epilogues
     assert 'c]' not in kernels[1] and 'w]' not in kernels[1] and 'n512' not in kernels[1], kernels[1]
     assert kernels[0] != kernels[2], kernels[2]
+    assert ',cl' not in kernels[1] and ',cl' not in kernels[3], kernels[3]
+    assert ',cl2>' in kernels[4] and ',cl4>' in kernels[5], (kernels[4], kernels[5])   # the depthwise half shared by a cluster
+    assert ',wmc2>' in kernels[6] and ',wmc4>' in kernels[7], (kernels[6], kernels[7]) # one weight stream multicast to a cluster
     if widths is synthetic.STOCK_WIDTHS:
-        assert 'n512x1' in kernels[0] and 'n512' not in kernels[2]
-    d1 = (outs[0].float() - outs[1].float()).abs().max().item()
-    d2 = (outs[0].float() - outs[2].float()).abs().max().item()
-    assert d1 == 0.0 and d2 == 0.0, (d1, d2, kernels[2])
+        assert 'n512x1' in kernels[3] and 'n512' not in kernels[2]
+    for i in range(1, len(outs)):
+        d = (outs[0].float() - outs[i].float()).abs().max().item()
+        assert d == 0.0, (i, d, kernels[i])
 
 
 def test_option_validation():

@@ -5,7 +5,7 @@ from fastdepth_b200 import synthetic
 from fastdepth_b200.engine import SkipAddEngine
 sd=synthetic.synthetic_state_dict()
 m=models.MobileNetSkipAdd((224,224),pretrained=False); m.load_state_dict(sd); m=m.eval().cuda().half()
-eng=SkipAddEngine(m); eng.set_option('graph',0); m.__dict__['_fd_engine']=eng
+eng=SkipAddEngine(m); eng.set_option('graph',0); eng.set_option('chain',int(__import__('os').environ.get('CHAIN','1'))); m.__dict__['_fd_engine']=eng
 x=synthetic.synthetic_input(64,224,224).cuda().half()
 plan=eng.plan_for(x)
 y=torch.empty((64,1,224,224),dtype=torch.half,device='cuda')
