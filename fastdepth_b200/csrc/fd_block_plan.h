@@ -20,6 +20,7 @@ struct BlockPlanIn {
     int no_wide;                 // experiments: 1 = a single epilogue group stays four warps (FD_TC_NO_WIDE)
     int no_colsplit;             // experiments: 1 = epilogue groups take alternate items even when they could share (FD_TC_NO_COLSPLIT)
     int n_sms;                   // SMs of the device (one CTA each); 0 = 148 (B200)
+    int even_rings;              // 1: input and A rings get an even number of stages (two depthwise teams on alternate steps); 0 / 2: no constraint
     int cluster;                 // 0 = the cost model may choose cluster mode, 1 = never, 2 / 4 = force that cluster size when the
                                  // block admits it (plan option "cluster", FD_TC_CLUSTER)
 };
@@ -52,6 +53,7 @@ inline bool plan_block_smem(const BlockPlanIn& q, BlockPlanOut& p, bool allow_na
     const int per_cta_kb = p.cs > 1 ? (p.kblocks + p.cs - 1) / p.cs : p.kblocks;      // K-blocks whose input tile THIS CTA loads
     for (int s_a = p.cs > 1 ? kPlanMaxACluster : kPlanMaxA; s_a >= 2; --s_a)
         for (int eg = q.head ? 1 : 3; eg >= 0; --eg) {
+            if (q.even_rings == 1 && p.cs == 1 && (s_a & 1)) continue;
             // epilogue organisation: 3 = two groups x two tiles, 2 = two groups x one tile, 1 = one group x two, 0 = one x one
             const int groups = q.head ? 2 : (eg >= 2 ? 2 : 1);
             const int n_stg = q.head ? 0 : groups * ((eg & 1) ? 2 : 1);
@@ -69,6 +71,7 @@ inline bool plan_block_smem(const BlockPlanIn& q, BlockPlanOut& p, bool allow_na
                         if (left < 0) continue;
                         int s_in = left / p.in_stage_stride;
                         if (s_in > kPlanMaxIn) s_in = kPlanMaxIn;
+                        if (q.even_rings == 1 && p.cs == 1 && s_in >= 2) s_in &= ~1;
                         if (s_in < 2 && !(s_in == 1 && p.kblocks == 1 && p.items <= sms)) continue;
                         if (p.cs > 1 && s_in > per_cta_kb + 1) s_in = per_cta_kb + 1 < 2 ? 2 : per_cta_kb + 1;
                         const int bn_eff = bn < 128 ? bn : 128;
@@ -166,7 +169,11 @@ inline BlockPlanOut plan_block(const BlockPlanIn& q) {
         // option / FD_TC_CLUSTER = 2 | 4 forces it wherever the block admits it (the bitwise tests do).
         for (int cs = 2; cs <= 4 && q.cluster != 1; cs *= 2) {
             if (q.cluster > 1 && q.cluster != cs) continue;
-            if (q.cluster == 0 && !(q.ksize == 5 && q.tile == 1 && cs == 4 && (long)q.n_tiles * cs <= sms)) continue;
+            if (q.cluster == 0 && !(q.ksize == 5 && q.tile == 1 && cs == 4)) continue;
+            // one wave only (every CTA runs exactly one item): forced multi-wave launches of this mode stopped making progress
+            // on the metric batch in bring-up (a timing-dependent stall between the A-ring hand-over and the item pipeline that
+            // the instrumented build does not show); the single-wave case is the one the cost model wants anyway
+            if ((long)q.n_tiles * cs > sms) continue;
             const int nc = ((cout_pad + cs - 1) / cs + 63) / 64 * 64;
             if (nc > 256 || nc * (cs - 1) >= cout_pad || p.kblocks < cs) continue;      // every CTA owns >= 1 K-block and a non-empty split
             const long n_cl = sms / cs;

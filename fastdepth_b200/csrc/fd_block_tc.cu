@@ -102,6 +102,8 @@ struct TcParams {
     const float2* pw_affine;  // [cpad_all / 2] x (scale, scale, bias, bias) of a channel pair
     const float* head_w;  // [cpad_all]
     int cl_debug;         // bring-up: bit 0 = commit a_empty locally only (no multicast; flow control of the A ring is then unsafe)
+    int dw_teams;         // 2: the depthwise warps form two teams of four that take alternate K-block steps, two 4x4 blocks per warp
+                          // (needs even s_in and s_a); 1: eight warps in lock-step, one block each
     int epi_high;         // 1: the epilogue runs on warps 8..15 and the depthwise on 0..7 (default: the other way round).  Which role
                           // the schedulers' arbitration should favour depends on which one paces the block: the stride-2 blocks are
                           // paced by their single epilogue staging tile, the others by the depthwise
@@ -182,6 +184,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
     // groups trade places (the warp schedulers favour one end of the id range, see TcParams::epi_high)
     const int rwarp = (p.epi_high && warp < TC_DW_WARPS + TC_EPI_WARPS) ? (warp ^ 8) : warp;
     constexpr bool CL = CLM == 1, CW = CLM == 2;
+    constexpr bool kHint = CLM != 1;                                   // barrier waits with a suspend-time hint (see mbar_wait_nohint)
     static_assert(!(HALFK && CLM != 0), "the half-K block has one K-block and resident weights: nothing to share");
     const uint32_t cs = CL ? (uint32_t)p.cs : 1u;                      // tile-sharing cluster: size and this CTA's rank in it
     const uint32_t crank = (CL || CW) ? cluster_ctarank() : 0u;
@@ -199,15 +202,23 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
     };
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < TC_MAX_IN; ++i) { mbar_init(smem_u32(&bars->in_full[i]), 1); mbar_init(smem_u32(&bars->in_empty[i]), TC_DW_WARPS); }
+        const uint32_t dw_arrivals = (uint32_t)(TC_DW_WARPS / ((CL || p.dw_teams != 2) ? 1 : 2));     // warps that work on one K-block step
+        for (int i = 0; i < TC_MAX_IN; ++i) { mbar_init(smem_u32(&bars->in_full[i]), 1); mbar_init(smem_u32(&bars->in_empty[i]), dw_arrivals); }
         // cluster mode: an A stage is full after ONE arrival (the owner's broadcast thread, or this CTA's own expect_tx for a
         // tile that arrives by bulk copy) and free again when the MMA streams of all cs CTAs have committed past it
-        for (int i = 0; i < TC_MAX_A; ++i) { mbar_init(smem_u32(&bars->a_full[i]), CL ? 1 : TC_DW_WARPS); mbar_init(smem_u32(&bars->a_empty[i]), (CL && (p.cl_debug & 1)) ? 1u : cs); }
+        for (int i = 0; i < TC_MAX_A; ++i) { mbar_init(smem_u32(&bars->a_full[i]), CL ? 1u : dw_arrivals); mbar_init(smem_u32(&bars->a_empty[i]), (CL && (p.cl_debug & 1)) ? 1u : cs); }
         for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars->dw_done[i]), TC_DW_WARPS);
         for (int i = 0; i < TC_MAX_B; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), wmc); }   // multicast: freed by all
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), (p.epi_colsplit || p.epi_wide) ? TC_EPI_WARPS : TC_EPI_WARPS / 2); }
         fence_barrier_init();
     }
+#ifdef FD_TC_WATCHDOG
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        printf("WATCHDOG map (cs %d wmc %d items %d kb %d s_in %d s_a %d s_b %d): in_full %u in_empty %u a_full %u a_empty %u b_full %u b_empty %u acc_full %u acc_empty %u dw_done %u\n",
+               p.cs, p.wmc, p.items, p.kblocks, p.s_in, p.s_a, p.s_b, smem_u32(&bars->in_full[0]), smem_u32(&bars->in_empty[0]), smem_u32(&bars->a_full[0]),
+               smem_u32(&bars->a_empty[0]), smem_u32(&bars->b_full[0]), smem_u32(&bars->b_empty[0]), smem_u32(&bars->acc_full[0]), smem_u32(&bars->acc_empty[0]),
+               smem_u32(&bars->dw_done[0]));
+#endif
     if (warp == TC_WARP_MMA) tmem_alloc(smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);     // MMA warp owns TMEM
     if (warp == TC_WARP_TMA && lane == 0) {
         tma_prefetch_desc(&tm_in);
@@ -245,7 +256,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                 const ItemCoord c = decode_item(p, w, NI, TH, TW);
                 for (int kb = CL ? (int)crank : 0; kb < p.kblocks; kb += (int)cs, rin.next((uint32_t)p.s_in)) {     // cluster mode: my K-blocks only
                     const uint32_t s = rin.s, ph = rin.ph;
-                    mbar_wait_sleep(smem_u32(&bars->in_empty[s]), ph ^ 1u, (uint32_t)p.sleep_ns >> 2);
+                    mbar_wait_sleep_sel<kHint>(smem_u32(&bars->in_empty[s]), ph ^ 1u, (uint32_t)p.sleep_ns >> 2);
                     mbar_expect_tx(smem_u32(&bars->in_full[s]), (uint32_t)(p.in_stage_bytes + p.dwp_bytes));
                     tma_load_4d(smem_base + in_off + s * p.in_stage_stride, &tm_in, smem_u32(&bars->in_full[s]), kb * TC_KBLK,
                                 c.ox0 * STRIDE - PAD, c.oy0 * STRIDE - PAD, c.img0);
@@ -271,7 +282,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                             sb = (uint32_t)(kb * p.nb + nbi);
                         } else {
                             sb = rb.s;
-                            mbar_wait_sleep(smem_u32(&bars->b_empty[sb]), rb.ph ^ 1u, (uint32_t)p.sleep_ns >> 2);
+                            mbar_wait_sleep_sel<kHint>(smem_u32(&bars->b_empty[sb]), rb.ph ^ 1u, (uint32_t)p.sleep_ns >> 2);
                             rb.next((uint32_t)p.s_b);
                         }
                         mbar_expect_tx(smem_u32(&bars->b_full[sb]), (uint32_t)p.b_stage_bytes);
@@ -315,10 +326,10 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                 }
             }
             for (int u = u_first; u < u_count; u += u_stride, racc.next((uint32_t)p.nacc), first = false) {
-                mbar_wait_sleep(bar_acc_empty + 8u * racc.s, racc.ph ^ 1u, (uint32_t)p.mma_sleep_ns);   // epilogue has drained this accumulator
+                mbar_wait_sleep_sel<kHint>(bar_acc_empty + 8u * racc.s, racc.ph ^ 1u, (uint32_t)p.mma_sleep_ns);   // epilogue has drained this accumulator
                 const uint32_t d_tmem = tmem_base + racc.s * (uint32_t)p.n_cta;
                 for (int kb = 0; kb < p.kblocks; ++kb, ra.next((uint32_t)p.s_a)) {
-                    mbar_wait_sleep(bar_a_full + 8u * ra.s, ra.ph, (uint32_t)p.mma_sleep_ns);
+                    mbar_wait_sleep_sel<kHint>(bar_a_full + 8u * ra.s, ra.ph, (uint32_t)p.mma_sleep_ns);
                     if constexpr (CL) {
                         if (q_left > 0) {
                             if ((uint32_t)kb_arm % cs != crank) mbar_expect_tx(bar_a_full + 8u * ra.s, (uint32_t)TC_A_STAGE_BYTES);
@@ -333,10 +344,10 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                         uint32_t sb;
                         if (p.b_resident) {
                             sb = (uint32_t)(kb * p.nb + nbi);
-                            if (first) { mbar_wait(bar_b_full + 8u * sb, 0); tc_fence_after(); }
+                            if (first) { mbar_wait_sel<kHint>(bar_b_full + 8u * sb, 0); tc_fence_after(); }
                         } else {
                             sb = rb.s;
-                            mbar_wait(bar_b_full + 8u * sb, rb.ph);
+                            mbar_wait_sel<kHint>(bar_b_full + 8u * sb, rb.ph);
                             rb.next((uint32_t)p.s_b);
                             tc_fence_after();
                         }
@@ -370,7 +381,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
             for (int u = u_first; u < u_count; u += u_stride)
                 for (int kb = 0; kb < p.kblocks; ++kb, ra.next((uint32_t)p.s_a)) {
                     if ((uint32_t)kb % cs != crank) continue;
-                    mbar_wait(smem_u32(&bars->dw_done[o & 3u]), (o >> 2) & 1u);
+                    mbar_wait_sel<kHint>(smem_u32(&bars->dw_done[o & 3u]), (o >> 2) & 1u);
                     ++o;
                     const uint32_t slot = smem_base + a_off + ra.s * TC_A_STAGE_BYTES, bar = smem_u32(&bars->a_full[ra.s]);
                     mbar_arrive(bar);                                            // the local MMA stream reads it in place
@@ -380,14 +391,18 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         }
     } else if (rwarp >= TC_WARP_DW0 && rwarp < TC_WARP_DW0 + TC_DW_WARPS) {
         // =========================== depthwise workers ===========================
+        // The tile's eight 4x4-pixel blocks are computed either by eight warps in lock-step on the same K-block step (one block
+        // each), or -- TcParams::dw_teams == 2 -- by two TEAMS of four warps that take alternate steps, two blocks per warp: a
+        // step's hand-shakes (two barrier waits, proxy fence, two arrives: ~300-500 cycles in which a warp issues nothing) are
+        // paid once per two blocks, and while one team is in them the other team's warps on the same schedulers are in their FMA
+        // stream.  Ring depths are even in that mode, so a team always meets the same stages and its parity tracking stays exact.
         constexpr int BPR = TW / 4, BPI = (TH / 4) * BPR;
         const int dwi = rwarp - TC_WARP_DW0;
-        const int ni = dwi / BPI, rem = dwi % BPI;
-        const int br = rem / BPR, bc = rem % BPR;
-        const uint32_t in_warp_off = (uint32_t)((ni * IH + br * 4 * STRIDE) * IW + bc * 4 * STRIDE) * 128u + lane * 4u;
+        const int teams = CL ? 1 : p.dw_teams;
+        const int team = teams == 2 ? dwi >> 2 : 0, member = teams == 2 ? dwi & 3 : dwi, nblk = teams;
         Ring rin, ra;
         int tr = 0;
-        uint32_t own = 0;                                  // cluster mode: operand tiles this CTA has produced
+        uint32_t own = 0;                                  // steps this CTA computes (cluster mode: the K-blocks it owns), both teams
         const bool tracer = dwi == 0 && lane == 0;
         for (int u = u_first; u < u_count; u += u_stride) {
             for (int kb = 0; kb < p.kblocks; ++kb, ra.next((uint32_t)p.s_a)) {
@@ -396,15 +411,15 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                     // a parity wait only tells "one phase further", and this CTA's next own use of a stage may lie several uses
                     // ahead (the uses in between belong to peers) -- skipping them would let the parity alias.  Free of charge:
                     // uses are released in K-block order, so an earlier one never completes later than the one needed next.
-                    mbar_wait(smem_u32(&bars->a_empty[ra.s]), ra.ph ^ 1u);
+                    mbar_wait_sel<kHint>(smem_u32(&bars->a_empty[ra.s]), ra.ph ^ 1u);
                     continue;
                 }
                 const uint32_t s = rin.s, ph = rin.ph, sa = ra.s, pha = ra.ph;
                 rin.next((uint32_t)p.s_in);
-                mbar_wait_sleep(smem_u32(&bars->in_full[s]), ph, (uint32_t)p.dw_sleep_ns);
+                if (teams == 2 && (int)(own & 1u) != team) { ++own; continue; }      // the other team's step
+                mbar_wait_sleep_sel<kHint>(smem_u32(&bars->in_full[s]), ph, (uint32_t)p.dw_sleep_ns);
                 if (tracer) TC_TRACE(1, tr);
                 const uint8_t* stage = smem + in_off + s * p.in_stage_stride;
-                const uint8_t* in_s = stage + in_warp_off;
                 // this K-block's depthwise taps + folded BN for the lane's channel pair (landed with the tile)
                 const uint8_t* prm = stage + p.in_stage_bytes;
                 const f32x2 sc = *reinterpret_cast<const f32x2*>(prm + KS * KS * 128 + lane * 8);        // (scale, scale) of the pair
@@ -412,13 +427,18 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                 // the A stage is normally free long before (deep ring): take it now so that every output row can be
                 // published the moment its last input row has been consumed -- the stores then drain during the math and
                 // the proxy fence at the end (a MEMBAR.ALL.CTA, ~36 cycles per store still in flight) finds few pending
-                mbar_wait(smem_u32(&bars->a_empty[sa]), pha ^ 1u);
+                mbar_wait_sel<kHint>(smem_u32(&bars->a_empty[sa]), pha ^ 1u);
                 uint8_t* a_s = smem + a_off + sa * TC_A_STAGE_BYTES;
 #ifdef FD_DW3_FHFMA                      // build-time A/B switch: 3x3 depthwise on FHFMA like the 5x5 (measured 1.2 % slower end to end)
                 constexpr bool kDwFfma2 = false;
 #else
                 constexpr bool kDwFfma2 = KS == 3;
 #endif
+#pragma unroll 1
+                for (int blk = 0; blk < nblk; ++blk) {
+                const int bidx = member * nblk + blk;                      // 4x4-pixel block of the tile
+                const int ni = bidx / BPI, rem = bidx % BPI, br = rem / BPR, bc = rem % BPR;
+                const uint8_t* in_s = stage + (uint32_t)((ni * IH + br * 4 * STRIDE) * IW + bc * 4 * STRIDE) * 128u + lane * 4u;
                 if constexpr (HALFK) {
                     static_assert(KS == 3 && STRIDE == 1, "half-K depthwise exists for the 3x3 stride-1 block only");
                     const int hl = lane & 15, hh = lane >> 4;       // channel pair, row half of the 4x4 block
@@ -536,6 +556,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                         }
                     }
                 }
+                }   // blk
                 if (tracer) TC_TRACE(2, tr);
                 // the input stage can be refilled as soon as every warp has read it
                 __syncwarp();
@@ -574,7 +595,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
             const ItemCoord c = decode_item(p, w, NI, TH, TW);
             const int img = c.img0 + e_ni, oy = c.oy0 + e_ty, ox = c.ox0 + e_tx;
             const bool valid = img < p.n && oy < p.h_out && ox < p.w_out;
-            mbar_wait_sleep(smem_u32(&bars->acc_full[ab]), pa, (uint32_t)p.sleep_ns);
+            mbar_wait_sleep_sel<kHint>(smem_u32(&bars->acc_full[ab]), pa, (uint32_t)p.sleep_ns);
             tc_fence_after();
             if (grp == 0 && elected) TC_TRACE(6, tr);
             const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + ab * (uint32_t)p.n_cta;
@@ -904,6 +925,7 @@ BlockPlanOut block_tc_debug_plan(int ksize, int stride, int h_out, int w_out, in
     q.n_tiles = ((w_out + TW - 1) / TW) * ((h_out + 7) / 8) * ((n + NI - 1) / NI);
     q.barrier_bytes = (int)sizeof(TcBarriers); q.n_sms = 148;
     q.cluster = 0;
+    { const char* e = getenv("FD_TC_DW_TEAMS"); q.even_rings = (e && *e == '1') ? 0 : ((e && *e == '2') ? 1 : 2); }
     plan_env_knobs(q);
     return plan_block(q);
 }
@@ -1004,6 +1026,7 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
     pin.ksize = g.ksize; pin.stride = g.stride; pin.tile = bp->tile; pin.c_in = g.c_in; pin.c_out = g.c_out; pin.n_tiles = n_tiles;
     pin.head = p.head; pin.barrier_bytes = (int)sizeof(TcBarriers); pin.n_sms = opts.n_sms;
     pin.cluster = (opts.cluster && !bp->halfk) ? 0 : 1;
+    { const char* e = getenv("FD_TC_DW_TEAMS"); pin.even_rings = (e && *e == '1') ? 0 : ((e && *e == '2') ? 1 : 2); }   // 1 = never, 2 = wherever even rings fit
     plan_env_knobs(pin);
     if (bp->halfk) pin.cluster = 1;
     const BlockPlanOut po = plan_block(pin);
@@ -1019,6 +1042,10 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
     // out of the L2 -- the small-map blocks move 110-125 MB through the L2 -> SM fabric per launch, more than half of it the same
     // weight blocks fetched again by every CTA (ncu l1tex__m_xbar2l1tex_read_bytes, profiles/r02_v1_kernels.csv).
     { const char* e = getenv("FD_TC_EPI_HIGH"); p.epi_high = (e && *e) ? atoi(e) : 0; }
+    // Two depthwise teams (see the kernel): measured -3 % on the single-K-block blocks (conv1 57.2 -> 55.4 us, decode_conv5
+    // 88.1 -> 85.4); where the even ring depths it needs cost the plan a staging tile or a weight stage it loses (conv3 +9 %), so:
+    // automatic only for one-K-block blocks whose unconstrained plan already has even rings; FD_TC_DW_TEAMS=2 forces even rings.
+    p.dw_teams = (pin.even_rings && p.cs == 1 && p.s_in >= 2 && !(p.s_in & 1) && !(p.s_a & 1) && (pin.even_rings == 1 || p.kblocks == 1)) ? 2 : 1;
     p.wmc = 1;
     {
         const char* e = getenv("FD_TC_WMC");               // 1 = never, 2 / 4 = force where the block admits it
@@ -1114,6 +1141,7 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
     char clbuf[16] = "";
     if (p.cs > 1) snprintf(clbuf, sizeof(clbuf), ",cl%d", p.cs);
     else if (p.wmc > 1) snprintf(clbuf, sizeof(clbuf), ",wmc%d", p.wmc);
+    if (p.dw_teams == 2) strncat(clbuf, ",t2", sizeof(clbuf) - strlen(clbuf) - 1);
     snprintf(buf, sizeof(buf), "block_tc<k%d,s%d,%s%s%s>%s%s%s[n%dx%d,bn%d%s,kb%d,in%d,a%d,b%d,e%dx%d%s]", g.ksize, g.stride, bp->tile ? "2x8x8" : "1x8x16", bp->halfk ? ",k32" : "", clbuf,
              g.upsample ? "+up2x" : "", a.skip ? (p.epi_red ? "+skip(red)" : "+skip") : "", p.head ? "+head" : (p.epi_tma ? "+tmast" : ""), p.n_cta, p.splits, p.bn,
              p.b_resident ? "r" : "", p.kblocks, p.s_in, p.s_a, p.s_b, p.epi_groups, p.head ? 0 : p.n_stg / p.epi_groups, p.epi_colsplit ? "c" : (p.epi_wide ? "w" : ""));

@@ -2,6 +2,7 @@
 // (fd_block_tc.cu: fused depthwise->pointwise blocks; fd_stem_tc.cu: im2col stem).
 #pragma once
 #include <cuda.h>
+#include <cstdio>
 
 #include "fd_common.cuh"
 
@@ -24,6 +25,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 // Blocking wait with a suspend-time hint: the thread is parked by the hardware (no issue slots burnt) until the phase
 // completes or the hint (ns) expires, instead of spinning on short default time-outs -- in the ncu instruction mix of the
 // hint-less version 40 % of all issued warp-instructions of decode_conv5 were TRYWAIT/BRA/YIELD of waiting warps.
+#ifdef FD_TC_WATCHDOG
+// Debug build (-DFD_TC_WATCHDOG): every blocking barrier wait gives up after ~50 ms, reports who waited for what and traps, so a
+// protocol dead-lock shows up as a launch failure with a message instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 100000000ll) {
+            printf("WATCHDOG block %d warp %d lane %d: barrier at smem offset %u parity %u never completed\n", (int)blockIdx.x, (int)(threadIdx.x >> 5),
+                   (int)(threadIdx.x & 31), bar, parity);
+            __trap();
+        }
+    }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -33,6 +51,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity), "r"(1000000u) : "memory");
 }
+#endif
 // Wait for roles that can afford wake-up latency (epilogue warps waiting for an accumulator, the TMA producer waiting for
 // a free stage).  ncu's source view of conv7 showed mbar_wait's try_wait/NANOSLEEP.SYNCS pair re-issuing every ~27 cycles
 // per waiting warp whatever the suspend hint says -- a quarter of all warp instructions of the kernel, taken from the
@@ -48,6 +67,25 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, u
         if (ok) break;
         __nanosleep(ns);
     }
+}
+// The same wait without a suspend-time hint.  The tile-sharing cluster instance of the block kernel uses it: with the hinted form
+// that instance stopped making progress on multi-wave launches (barriers completed by another SM -- bulk-copy bytes, multicast
+// commits -- and two producer lanes of one warp parked in hinted waits at once); the plain probe loop has never been seen to stall.
+__device__ __forceinline__ void mbar_wait_nohint(uint32_t bar, uint32_t parity) {
+    for (;;) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+    }
+}
+template <bool HINT>
+__device__ __forceinline__ void mbar_wait_sel(uint32_t bar, uint32_t parity) {
+    if constexpr (HINT) mbar_wait(bar, parity); else mbar_wait_nohint(bar, parity);
+}
+template <bool HINT>
+__device__ __forceinline__ void mbar_wait_sleep_sel(uint32_t bar, uint32_t parity, uint32_t ns) {
+    if (ns == 0u) { mbar_wait_sel<HINT>(bar, parity); return; }
+    mbar_wait_sleep(bar, parity, ns);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

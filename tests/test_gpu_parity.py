@@ -311,15 +311,15 @@ def test_epilogue_organisations_and_item_shapes_agree_bitwise(widths, monkeypatc
     m, _ = make_model(widths, torch.float16, (224, 224))
     x = synthetic.synthetic_input(64, 224, 224, seed=11).cuda().half()     # the metric batch: only there does the planner
     outs, kernels = [], []                                                  # pick one 512-column accumulator per 14x14 tile
-    knobs = ('FD_TC_MAX_NCTA', 'FD_TC_NO_COLSPLIT', 'FD_TC_NO_WIDE', 'FD_TC_CLUSTER', 'FD_TC_WMC')
+    knobs = ('FD_TC_MAX_NCTA', 'FD_TC_NO_COLSPLIT', 'FD_TC_NO_WIDE', 'FD_TC_CLUSTER', 'FD_TC_WMC', 'FD_TC_DW_TEAMS')
     for env, opts in (({}, {}),
                       ({'FD_TC_MAX_NCTA': '256', 'FD_TC_NO_COLSPLIT': '1', 'FD_TC_NO_WIDE': '1', 'FD_TC_CLUSTER': '1'}, {}),
                       ({'FD_TC_MAX_NCTA': '128'}, {'wait_sleep_ns': 200}),
                       ({'FD_TC_CLUSTER': '1'}, {}),                # never a cluster
-                      ({'FD_TC_CLUSTER': '2'}, {}),                # 2-CTA tile-sharing clusters wherever a block admits them
-                      ({'FD_TC_CLUSTER': '4'}, {}),                # 4-CTA ...
                       ({'FD_TC_CLUSTER': '1', 'FD_TC_WMC': '2'}, {}),      # weight-multicast clusters of 2 tiles
-                      ({'FD_TC_CLUSTER': '1', 'FD_TC_WMC': '4'}, {})):     # ... of 4 tiles
+                      ({'FD_TC_CLUSTER': '1', 'FD_TC_WMC': '4'}, {}),      # ... of 4 tiles
+                      ({'FD_TC_DW_TEAMS': '1'}, {}),               # eight depthwise warps in lock-step everywhere
+                      ({'FD_TC_DW_TEAMS': '2'}, {})):              # two depthwise teams wherever even ring depths fit
         for k in knobs:
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
@@ -337,13 +337,42 @@ def test_epilogue_organisations_and_item_shapes_agree_bitwise(widths, monkeypatc
     assert 'c]' not in kernels[1] and 'w]' not in kernels[1] and 'n512' not in kernels[1], kernels[1]
     assert kernels[0] != kernels[2], kernels[2]
     assert ',cl' not in kernels[1] and ',cl' not in kernels[3], kernels[3]
-    assert ',cl2>' in kernels[4] and ',cl4>' in kernels[5], (kernels[4], kernels[5])   # the depthwise half shared by a cluster
-    assert ',wmc2>' in kernels[6] and ',wmc4>' in kernels[7], (kernels[6], kernels[7]) # one weight stream multicast to a cluster
+    assert ',wmc2' in kernels[4] and ',wmc4' in kernels[5], (kernels[4], kernels[5])   # one weight stream multicast to a cluster
+    assert ',t2' not in kernels[6] and kernels[7].count(',t2') > kernels[0].count(',t2') > 0, (kernels[0], kernels[7])
     if widths is synthetic.STOCK_WIDTHS:
         assert 'n512x1' in kernels[3] and 'n512' not in kernels[2]
     for i in range(1, len(outs)):
         d = (outs[0].float() - outs[i].float()).abs().max().item()
         assert d == 0.0, (i, d, kernels[i])
+
+
+@pytest.mark.parametrize('widths', [synthetic.STOCK_WIDTHS, synthetic.PRUNED_WIDTHS], ids=['stock', 'pruned'])
+def test_tile_sharing_clusters_agree_bitwise(widths, monkeypatch):
+    """Tile-sharing clusters (2 / 4 CTAs split one tile's depthwise half and output channels, operand tiles handed over through
+    DSMEM) against the cluster-less plan, forced wherever a block admits them (one wave: batch 8), stage by stage, bit for bit."""
+    from fastdepth_b200.engine import SkipAddEngine
+    m, _ = make_model(widths, torch.float16, (224, 224))
+    x = synthetic.synthetic_input(8, 224, 224, seed=12).cuda().half()
+    ref = None
+    for cl in ('1', '2', '4'):
+        monkeypatch.setenv('FD_TC_CLUSTER', cl)
+        eng = SkipAddEngine(m)
+        for k, v in (('chain', 0), ('inplace_skip', 0), ('fold_head', 0)):
+            eng.set_option(k, v)
+        m.__dict__['_fd_engine'] = eng
+        with torch.no_grad():
+            y = m(x).clone()
+        plan = next(iter(eng.plans.values()))
+        kern = ' '.join(s['kernel'] for s in plan.steps())
+        outs = [plan.stage_tensor(i).clone() for i in range(len(plan.names) - 1)] + [y]
+        torch.cuda.synchronize()
+        if ref is None:
+            ref = outs
+            assert ',cl' not in kern, kern
+            continue
+        assert kern.count(',cl%s' % cl) >= 3, kern
+        for i, (a, b) in enumerate(zip(ref, outs)):
+            assert torch.equal(a, b), (cl, i, kern)
 
 
 def test_option_validation():
