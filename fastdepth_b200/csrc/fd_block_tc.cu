@@ -434,6 +434,12 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
 #else
                 constexpr bool kDwFfma2 = KS == 3;
 #endif
+                // 5x5: the 25 tap words of the lane's channel pair, once per step (shared by both blocks of a team warp)
+                uint32_t wv[(HALFK || kDwFfma2) ? 1 : KS * KS];
+                if constexpr (!HALFK && !kDwFfma2) {
+#pragma unroll
+                    for (int i = 0; i < KS * KS; ++i) wv[i] = *reinterpret_cast<const uint32_t*>(prm + i * 128 + lane * 4);
+                }
 #pragma unroll 1
                 for (int blk = 0; blk < nblk; ++blk) {
                 const int bidx = member * nblk + blk;                      // 4x4-pixel block of the tile
@@ -523,9 +529,6 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                     // 5x5 stays on the mixed-precision FHFMA (16-bit x 16-bit + fp32, exact products): tools/fma2_tput5.cu under
                     // this kernel's register cap gives 2 118 cycles per 4x4 block for 800 FHFMA (~0.76 / clk / scheduler, close
                     // to full rate) against 2 720 for 400 FFMA2 + 178 HADD2, and in the kernel decode_conv5 went 88 -> 109 us
-                    uint32_t wv[KS * KS];
-#pragma unroll
-                    for (int i = 0; i < KS * KS; ++i) wv[i] = *reinterpret_cast<const uint32_t*>(prm + i * 128 + lane * 4);
                     float acc[4][4][2];
 #pragma unroll
                     for (int a = 0; a < 4; ++a)
@@ -926,6 +929,7 @@ BlockPlanOut block_tc_debug_plan(int ksize, int stride, int h_out, int w_out, in
     q.barrier_bytes = (int)sizeof(TcBarriers); q.n_sms = 148;
     q.cluster = 0;
     { const char* e = getenv("FD_TC_DW_TEAMS"); q.even_rings = (e && *e == '1') ? 0 : ((e && *e == '2') ? 1 : 2); }
+    if (q.even_rings == 2 && ksize == 5 && (c_in + TC_KBLK - 1) / TC_KBLK <= 2) q.even_rings = 1;
     plan_env_knobs(q);
     return plan_block(q);
 }
@@ -1027,6 +1031,7 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
     pin.head = p.head; pin.barrier_bytes = (int)sizeof(TcBarriers); pin.n_sms = opts.n_sms;
     pin.cluster = (opts.cluster && !bp->halfk) ? 0 : 1;
     { const char* e = getenv("FD_TC_DW_TEAMS"); pin.even_rings = (e && *e == '1') ? 0 : ((e && *e == '2') ? 1 : 2); }   // 1 = never, 2 = wherever even rings fit
+    if (pin.even_rings == 2 && g.ksize == 5 && (g.c_in + TC_KBLK - 1) / TC_KBLK <= 2) pin.even_rings = 1;   // decode_conv4: in4/a2 + teams 59.4 -> 57.5 us
     plan_env_knobs(pin);
     if (bp->halfk) pin.cluster = 1;
     const BlockPlanOut po = plan_block(pin);
