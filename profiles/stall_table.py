@@ -5,7 +5,8 @@ import csv
 import subprocess
 import sys
 
-NAMES = ['conv%d' % i for i in range(14)] + ['decode_conv%d' % j for j in range(1, 6)]
+NAMES = ['conv%d' % i for i in range(14)] + ['decode_conv%d' % j for j in range(1, 6)]                          # round 1: 19 launches
+NAMES_R2 = ['conv%d' % i for i in range(7)] + ['conv7..conv11', 'conv12', 'conv13'] + ['decode_conv%d' % j for j in range(1, 6)]   # chain kernel: 15
 
 
 def one(rep, i):
@@ -38,7 +39,7 @@ def main(rep, out):
                 '`barrier` are mostly warps parked on an mbarrier or the final `__syncthreads`, `selected` + `not_selected` are\n'
                 'warps that could issue).  Opcode column: where the samples sit.\n\n'
                 '| stage | samples | warp-instr | top stall reasons (%) | top opcodes by samples (%) |\n|---|---:|---:|---|---|\n')
-        for i, name in enumerate(NAMES):
+        for i, name in enumerate(NAMES_R2 if len(sys.argv) > 3 and sys.argv[3] == 'r2' else NAMES):
             tot, instr, st, op = one(rep, i)
             f.write('| %s | %d | %.1f M | %s | %s |\n' % (
                 name, tot, instr / 1e6,

@@ -1,0 +1,25 @@
+#!/bin/bash
+# final r02 evidence: bench line, launch list, ncu full capture of one forward, timelines, sanitizer, other configurations
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+timeout 600 python bench.py > gpurun_out/f_bench.json 2> gpurun_out/f_bench.err; tail -c 300 gpurun_out/f_bench.err
+B="python bench.py --steps 2 --warmup 3 --graph 0 --no-cpu-baseline --no-lib-baseline --no-eval --stage-iters 1 --e2e-steps 6"
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"chain_tc|block_tc|stem_tc" --launch-skip 30 --launch-count 30 --csv --log-file gpurun_out/f_launches.csv $B > gpurun_out/f_ncu_launch.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"chain_tc|block_tc|stem_tc" --launch-skip 30 --launch-count 15 -o gpurun_out/prof_r2f $B > gpurun_out/f_ncu_full.log 2>&1
+ls -la gpurun_out/prof_r2f.ncu-rep
+timeout 200 python tools/trace_chain.py > gpurun_out/f_trace_chain.txt 2>&1
+timeout 300 python tools/trace_stage.py 1 2 3 5 12 13 14 17 18 > gpurun_out/f_trace.txt 2>&1
+for cfg in "--widths pruned" "--batch 32" "--dtype bf16" "--hw 480 640 --batch 16"; do
+  timeout 300 python bench.py $cfg --no-cpu-baseline --no-lib-baseline --no-eval --e2e-steps 60 > "gpurun_out/f_bench_$(echo $cfg | tr -d ' -').json" 2>> gpurun_out/f_bench.err
+done
+for tool in memcheck synccheck racecheck; do
+  timeout 420 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_run.py quick > gpurun_out/f_san_$tool.txt 2>&1; echo "rc=$?" >> gpurun_out/f_san_$tool.txt
+  tail -n 3 gpurun_out/f_san_$tool.txt
+done
+python -c "
+import json,glob
+for f in sorted(glob.glob('gpurun_out/f_bench*.json')):
+    try:
+        d=json.load(open(f)); print(f, round(d['value']), round(d['e2e']['value']), d['roofline']['bound'], round(d['roofline']['frac'],3), d['parity']['max_rel_err_vs_oracle'])
+    except Exception as e: print(f, 'ERR', e)
+"
