@@ -21,6 +21,7 @@ struct BlockPlanIn {
     int no_colsplit;             // experiments: 1 = epilogue groups take alternate items even when they could share (FD_TC_NO_COLSPLIT)
     int n_sms;                   // SMs of the device (one CTA each); 0 = 148 (B200)
     int even_rings;              // 1: input and A rings get an even number of stages (two depthwise teams on alternate steps); 0 / 2: no constraint
+    int cluster_multiwave;       // bring-up only (FD_TC_CLUSTER_MULTIWAVE=1): admit tile-sharing clusters on multi-wave launches
     int cluster;                 // 0 = the cost model may choose cluster mode, 1 = never, 2 / 4 = force that cluster size when the
                                  // block admits it (plan option "cluster", FD_TC_CLUSTER)
 };
@@ -173,7 +174,7 @@ inline BlockPlanOut plan_block(const BlockPlanIn& q) {
             // one wave only (every CTA runs exactly one item): forced multi-wave launches of this mode stopped making progress
             // on the metric batch in bring-up (a timing-dependent stall between the A-ring hand-over and the item pipeline that
             // the instrumented build does not show); the single-wave case is the one the cost model wants anyway
-            if ((long)q.n_tiles * cs > sms) continue;
+            if ((long)q.n_tiles * cs > sms && !q.cluster_multiwave) continue;
             const int nc = ((cout_pad + cs - 1) / cs + 63) / 64 * 64;
             if (nc > 256 || nc * (cs - 1) >= cout_pad || p.kblocks < cs) continue;      // every CTA owns >= 1 K-block and a non-empty split
             const long n_cl = sms / cs;

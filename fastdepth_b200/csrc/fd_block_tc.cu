@@ -212,7 +212,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), (p.epi_colsplit || p.epi_wide) ? TC_EPI_WARPS : TC_EPI_WARPS / 2); }
         fence_barrier_init();
     }
-#ifdef FD_TC_WATCHDOG
+#ifdef FD_TC_WATCHDOG_MAP
     if (blockIdx.x == 0 && threadIdx.x == 0)
         printf("WATCHDOG map (cs %d wmc %d items %d kb %d s_in %d s_a %d s_b %d): in_full %u in_empty %u a_full %u a_empty %u b_full %u b_empty %u acc_full %u acc_empty %u dw_done %u\n",
                p.cs, p.wmc, p.items, p.kblocks, p.s_in, p.s_a, p.s_b, smem_u32(&bars->in_full[0]), smem_u32(&bars->in_empty[0]), smem_u32(&bars->a_full[0]),
@@ -817,6 +817,7 @@ static void plan_env_knobs(BlockPlanIn& q) {
     const char* c = getenv("FD_TC_NO_WIDE");
     const char* d = getenv("FD_TC_CLUSTER");          // 1 = never, 2 / 4 = force that cluster size where the block admits it
     if (d && *d) q.cluster = atoi(d);
+    { const char* m = getenv("FD_TC_CLUSTER_MULTIWAVE"); q.cluster_multiwave = (m && *m == '1') ? 1 : 0; }
     q.no_wide = (c && *c == '1') ? 1 : 0;
     q.max_n_cta = a ? atoi(a) : 0;
     q.no_colsplit = (b && *b == '1') ? 1 : 0;

@@ -68,15 +68,23 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, u
         __nanosleep(ns);
     }
 }
-// The same wait without a suspend-time hint.  The tile-sharing cluster instance of the block kernel uses it: with the hinted form
-// that instance stopped making progress on multi-wave launches (barriers completed by another SM -- bulk-copy bytes, multicast
-// commits -- and two producer lanes of one warp parked in hinted waits at once); the plain probe loop has never been seen to stall.
+// A plain probe loop with a pause between probes, used by the tile-sharing cluster instance of the block kernel (its waiters
+// sit on barriers that are completed from OTHER SMs: bulk-copy bytes, multicast commits).  Bring-up record: forced onto multi-wave
+// launches that instance stalls with the hinted wait, with this loop and with back-to-back probes alike (8 of 8 runs), while the
+// library built with -DFD_TC_WATCHDOG (same loop plus a clock read per probe) ran through 4 of 4 times with correct results --
+// a timing-dependent interaction that is NOT root-caused; the planner therefore admits that mode on one-wave launches only
+// (FD_TC_CLUSTER_MULTIWAVE=1 lifts the limit for further bring-up).
 __device__ __forceinline__ void mbar_wait_nohint(uint32_t bar, uint32_t parity) {
+#ifdef FD_TC_WATCHDOG
+    mbar_wait(bar, parity);          // the watchdog form is a plain probe loop already
+#else
     for (;;) {
         uint32_t ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
         if (ok) return;
+        __nanosleep(40);
     }
+#endif
 }
 template <bool HINT>
 __device__ __forceinline__ void mbar_wait_sel(uint32_t bar, uint32_t parity) {
