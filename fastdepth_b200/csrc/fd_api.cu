@@ -798,6 +798,7 @@ int fd_debug_block_plan(int ksize, int stride, int h_out, int w_out, int n, int 
     if (cap >= 18) { out[16] = q.nacc; out[17] = q.epi_colsplit; }
     if (cap >= 19) out[18] = q.epi_wide;
     if (cap >= 20) out[19] = q.cs;
+    if (cap >= 21) out[20] = q.dw_teams;
     return FD_OK;
 }
 

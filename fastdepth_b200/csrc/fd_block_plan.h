@@ -34,6 +34,7 @@ struct BlockPlanOut {
     int nacc;                    // TMEM accumulators: 2 of n_cta <= 256 columns, or 1 of up to 512
     int epi_colsplit;            // 1: both epilogue groups drain every item, alternating 64-column blocks
     int epi_wide;                // 1: one staging tile, all eight epilogue warps on it (32 columns per warp)
+    int dw_teams;                // 2: two depthwise teams of four warps on alternate K-block steps (needs even s_in and s_a), else 1
     int cs;                      // cluster size: 1, or 2 / 4 CTAs that share one tile -- CTA r computes the depthwise half of the
                                  // K-blocks kb % cs == r, broadcasts its operand tiles to the others through DSMEM and runs the MMAs
                                  // of output-channel split r (splits == cs)
@@ -111,6 +112,12 @@ inline bool plan_block_smem(const BlockPlanIn& q, BlockPlanOut& p, bool allow_na
     // block's 64 columns -- these blocks were bound by a single four-warp group draining 3 400 cycles per block
     p.epi_wide = (!q.head && p.epi_groups == 1 && !q.no_wide) ? 1 : 0;
     return true;
+}
+
+// two depthwise teams: asked for (even_rings 1 = wherever even rings fit, 2 = only where the plan is even anyway and the block
+// has a single K-block), not on a tile-sharing cluster, and the rings really are even
+inline int plan_dw_teams(const BlockPlanIn& q, const BlockPlanOut& p) {
+    return (q.even_rings && p.cs == 1 && p.s_in >= 2 && !(p.s_in & 1) && !(p.s_a & 1) && (q.even_rings == 1 || p.kblocks == 1)) ? 2 : 1;
 }
 
 inline BlockPlanOut plan_block(const BlockPlanIn& q) {
@@ -199,7 +206,7 @@ inline BlockPlanOut plan_block(const BlockPlanIn& q) {
         p.nacc = p.n_cta > 256 ? 1 : 2;
         p.tmem_cols = 32;
         while (p.tmem_cols < p.nacc * p.n_cta) p.tmem_cols *= 2;
-        if (plan_block_smem(q, p, false)) { p.ok = 1; return p; }
+        if (plan_block_smem(q, p, false)) { p.ok = 1; p.dw_teams = plan_dw_teams(q, p); return p; }
     }
     for (int i = 0; i < n_cands; ++i) {                              // nothing fits with full-width MMAs: accept narrow ones
         p.splits = cands[i].sp; p.n_cta = cands[i].nc; p.cs = cands[i].cs;
@@ -208,7 +215,7 @@ inline BlockPlanOut plan_block(const BlockPlanIn& q) {
         p.nacc = p.n_cta > 256 ? 1 : 2;
         p.tmem_cols = 32;
         while (p.tmem_cols < p.nacc * p.n_cta) p.tmem_cols *= 2;
-        if (plan_block_smem(q, p, true)) { p.ok = 1; return p; }
+        if (plan_block_smem(q, p, true)) { p.ok = 1; p.dw_teams = plan_dw_teams(q, p); return p; }
     }
     p.ok = 0;
     return p;

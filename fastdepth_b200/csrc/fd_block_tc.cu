@@ -1051,7 +1051,7 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
     // Two depthwise teams (see the kernel): measured -3 % on the single-K-block blocks (conv1 57.2 -> 55.4 us, decode_conv5
     // 88.1 -> 85.4); where the even ring depths it needs cost the plan a staging tile or a weight stage it loses (conv3 +9 %), so:
     // automatic only for one-K-block blocks whose unconstrained plan already has even rings; FD_TC_DW_TEAMS=2 forces even rings.
-    p.dw_teams = (pin.even_rings && p.cs == 1 && p.s_in >= 2 && !(p.s_in & 1) && !(p.s_a & 1) && (pin.even_rings == 1 || p.kblocks == 1)) ? 2 : 1;
+    p.dw_teams = po.dw_teams;
     p.wmc = 1;
     {
         const char* e = getenv("FD_TC_WMC");               // 1 = never, 2 / 4 = force where the block admits it

@@ -173,7 +173,7 @@ int fd_plan_trace_stage(fd_plan* plan, int stage, void* y_dev, void* stream,
 /* Debug (host only, needs no GPU): the shared-memory / pipeline plan the fused block kernel would use for one
  * block.  out[0..15] = {ok, splits, n_cta, items, kblocks, s_in, s_a, s_b, bn, nb, b_resident, epi_groups, n_stg,
  * smem_bytes, tmem_cols, in_stage_stride}; with cap >= 18 also out[16..17] = {nacc (TMEM accumulators), epi_colsplit},
- * with cap >= 19 out[18] = epi_wide, with cap >= 20 out[19] = cs (cluster size: CTAs sharing one tile's depthwise half).
+ * with cap >= 19 out[18] = epi_wide, with cap >= 20 out[19] = cs (cluster size: CTAs sharing one tile's depthwise half), with cap >= 21 out[20] = dw_teams.
  * cap must be at least 16. */
 int fd_debug_block_plan(int ksize, int stride, int h_out, int w_out, int n, int c_in, int c_out, int head,
                         int* out, int cap);

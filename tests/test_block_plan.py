@@ -8,14 +8,14 @@ import pytest
 from fastdepth_b200 import _lib, synthetic
 
 KEYS = ('ok', 'splits', 'n_cta', 'items', 'kblocks', 's_in', 's_a', 's_b', 'bn', 'nb', 'b_resident', 'epi_groups',
-        'n_stg', 'smem_bytes', 'tmem_cols', 'in_stage_stride', 'nacc', 'epi_colsplit', 'epi_wide', 'cs')
+        'n_stg', 'smem_bytes', 'tmem_cols', 'in_stage_stride', 'nacc', 'epi_colsplit', 'epi_wide', 'cs', 'dw_teams')
 STRIDES = (2, 1, 2, 1, 2, 1, 2, 1, 1, 1, 1, 1, 2, 1)
 
 
 def plan(ks, stride, h, w, n, cin, cout, head=0):
     lib = _lib.load()
-    out = (ctypes.c_int * 20)()
-    _lib.check(lib.fd_debug_block_plan(ks, stride, h, w, n, cin, cout, head, out, 20))
+    out = (ctypes.c_int * 21)()
+    _lib.check(lib.fd_debug_block_plan(ks, stride, h, w, n, cin, cout, head, out, 21))
     return dict(zip(KEYS, out))
 
 
@@ -59,7 +59,13 @@ def test_stock_b64_plans_snapshot(built_lib):
     # one 512-column accumulator per tile: the depthwise half and the input tile are not repeated per split
     assert p['splits'] == 1 and p['n_cta'] == 512 and p['nacc'] == 1 and p['bn'] == 256 and p['epi_colsplit'] == 1
     p = plan(5, 1, 112, 112, 64, 64, 32, head=1)  # decode_conv5 + folded head
-    assert p['n_stg'] == 0 and p['splits'] == 1
+    assert p['n_stg'] == 0 and p['splits'] == 1 and p['dw_teams'] == 2       # one K-block, even rings: two depthwise teams
+    p = plan(5, 1, 7, 7, 64, 1024, 512)           # decode_conv1: 32 tiles x 4 CTAs in one wave share the 5x5 depthwise half
+    assert p['cs'] == 4 and p['splits'] == 4 and p['n_cta'] == 128 and p['dw_teams'] == 1
+    p = plan(3, 1, 7, 7, 64, 1024, 1024)          # conv13: paced by its weight stream once the depthwise is shared -> no cluster
+    assert p['cs'] == 1
+    p = plan(5, 1, 7, 7, 512, 1024, 512)          # same block at batch 512: more than one wave -> no tile sharing
+    assert p['cs'] == 1
 
 
 def test_planner_invariants_on_random_blocks(built_lib):
@@ -99,5 +105,7 @@ def test_planner_invariants_on_random_blocks(built_lib):
             assert not p['epi_wide'] or p['epi_groups'] == 1, ctx
             assert p['nacc'] == 2 or p['epi_colsplit'], ctx                        # one accumulator: both groups must drain it
         assert p['nacc'] == 2 or p['items'] <= 148, ctx                            # ... and no CTA runs two items on it
+        assert p['cs'] == 1 or p['items'] <= 148, ctx                              # tile-sharing clusters: one wave only
+        assert p['dw_teams'] in (1, 2) and (p['dw_teams'] == 1 or (p['cs'] == 1 and p['s_in'] % 2 == 0 and p['s_a'] % 2 == 0)), ctx
 
     check()
