@@ -121,6 +121,7 @@ struct TcBarriers {
     uint64_t a_full[TC_MAX_A], a_empty[TC_MAX_A];
     uint64_t b_full[TC_MAX_B], b_empty[TC_MAX_B];
     uint64_t acc_full[2], acc_empty[2];
+    uint64_t aff_full;    // the pointwise BN affine has landed in shared memory (one bulk copy issued in the prologue)
     uint64_t dw_done[4];  // cluster mode: the depthwise warps have finished (and proxy-fenced) an operand tile -> broadcast thread
     uint32_t tmem_base;
     uint32_t pad;
@@ -210,7 +211,12 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars->dw_done[i]), TC_DW_WARPS);
         for (int i = 0; i < TC_MAX_B; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), wmc); }   // multicast: freed by all
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), (p.epi_colsplit || p.epi_wide) ? TC_EPI_WARPS : TC_EPI_WARPS / 2); }
+        mbar_init(smem_u32(&bars->aff_full), 1);
         fence_barrier_init();
+        // the pointwise BN affine (constant data, independent of the previous kernel) comes in as ONE asynchronous bulk copy that the
+        // epilogue warps wait for before their first tile, instead of a strided copy loop of all threads on the start-up path
+        mbar_expect_tx(smem_u32(&bars->aff_full), (uint32_t)p.cpad_all * 8u);
+        bulk_load(smem_base + pw_off, p.pw_affine, (uint32_t)p.cpad_all * 8u, smem_u32(&bars->aff_full));
     }
 #ifdef FD_TC_WATCHDOG_MAP
     if (blockIdx.x == 0 && threadIdx.x == 0)
@@ -225,10 +231,8 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         tma_prefetch_desc(&tm_w);
         if (p.epi_tma) { tma_prefetch_desc(&tm_o0); if (p.upsample) { tma_prefetch_desc(&tm_o1); tma_prefetch_desc(&tm_o2); tma_prefetch_desc(&tm_o3); } }
     }
-    for (int i = threadIdx.x; i < p.cpad_all; i += (int)blockDim.x) {      // pointwise BN affine (+ head weights) -> smem
-        s_pw_affine[i] = p.pw_affine[i];
-        if (p.head && !(i & 1)) s_head_w2[i >> 1] = MF::pack(p.head_w[i], p.head_w[i + 1]);   // cpad_all is even
-    }
+    if (p.head)                                                            // head weights of a channel pair, 16-bit x 2 (cpad_all is even)
+        for (int i = 2 * threadIdx.x; i < p.cpad_all; i += 2 * (int)blockDim.x) s_head_w2[i >> 1] = MF::pack(p.head_w[i], p.head_w[i + 1]);
     if constexpr (HALFK) {
         // channels 32..63 of every A row are never written by the depthwise warps: zero the stages once (their products meet
         // the zero-filled K rows of the weights, but 0 x NaN from uninitialised shared memory would still poison the sum)
@@ -592,6 +596,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         uint32_t ab = (ngrp == 2 && !cs) ? (uint32_t)grp : 0u, pa = 0;   // accumulator buffer and its mbarrier phase
         int tr = 0;
         uint32_t stg_flip = 0;
+        mbar_wait_sel<kHint>(smem_u32(&bars->aff_full), 0);      // BN affine in place (bulk copy of the prologue)
         const int u_step = (cs ? 1 : ngrp) * u_stride;
         for (int u = u_first + ((cs || wide) ? 0 : grp) * u_stride; (grp < ngrp || wide) && u < u_count; u += u_step) {
             const int w = item_of(u);
