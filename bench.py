@@ -322,6 +322,8 @@ def run_reference(args, rank):
     h, w = args.hw
     # torchrun exports OMP_NUM_THREADS=1 for every worker; the reference arm is meant to use all host threads it can
     cores, thread_note = pick_cpu_threads(sd, h, w)
+    # batch <= 8 per step on purpose: that is where the CPU forward is fastest per image (batch 64 measured 31 img/s against 77-240
+    # at batch 8 on the same cores: the activations fall out of the caches), and the reference arm should be the reference at its best
     rate, batch, steps, per = cpu_forward_rate(sd, h, w, budget_s=0, min_steps=max(1, args.steps), warmup=max(1, args.warmup))
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
