@@ -9,7 +9,16 @@ constexpr int kPlanAStage = 128 * 128;       // one A operand stage: 128 rows x 
 constexpr int kPlanStg = 16384;              // one epilogue staging tile: 128 px x 64 ch x 2 B
 constexpr int kPlanMaxIn = 6, kPlanMaxA = 4, kPlanMaxB = 16;
 constexpr int kPlanMaxACluster = 6;          // cluster mode: the A ring is filled by several CTAs at once and wants >= cluster size stages
-constexpr int kPlanSmemBudget = 224 * 1024;  // of the 227 KB a CTA may use (alignment slack is budgeted separately)
+#ifndef FD_PLAN_SMALL_SMEM
+// everything that needs 1 KB alignment sits in front of the 128-byte-granular input stages (see the kernel's carve-up): ONE alignment
+// slack, and the budget is the whole 227 KB minus a small margin (round 1: 224 KB and two slacks -- conv2 missed its second staging
+// tile by 8 bytes)
+constexpr int kPlanSmemBudget = 227 * 1024 - 128;
+constexpr int kPlanAlignSlack = 1024;
+#else
+constexpr int kPlanSmemBudget = 224 * 1024;
+constexpr int kPlanAlignSlack = 2048;
+#endif
 
 struct BlockPlanIn {
     int ksize, stride, tile;     // tile: 0 = 1 image x 8 x 16, 1 = 2 images x 8 x 8
@@ -47,7 +56,7 @@ struct BlockPlanOut {
 inline bool plan_block_smem(const BlockPlanIn& q, BlockPlanOut& p, bool allow_narrow) {
     const int splits = p.splits;
     const int sms = q.n_sms > 0 ? q.n_sms : 148;
-    const int fixed = q.barrier_bytes + 2048 + (q.head ? 3 : 2) * p.cpad_all * 4;      // 2048: two 1 KB alignment slacks
+    const int fixed = q.barrier_bytes + kPlanAlignSlack + (q.head ? 3 : 2) * p.cpad_all * 4;
     const int total = kPlanSmemBudget - fixed;
     long best = -(1L << 60);
     bool found = false;
@@ -74,6 +83,7 @@ inline bool plan_block_smem(const BlockPlanIn& q, BlockPlanOut& p, bool allow_na
                         int s_in = left / p.in_stage_stride;
                         if (s_in > kPlanMaxIn) s_in = kPlanMaxIn;
                         if (q.even_rings == 1 && p.cs == 1 && s_in >= 2) s_in &= ~1;
+                        if (q.even_rings && p.cs == 1 && s_in > 4) s_in &= ~1;        // beyond four stages depth buys nothing: keep the ring even
                         if (s_in < 2 && !(s_in == 1 && p.kblocks == 1 && p.items <= sms)) continue;
                         if (p.cs > 1 && s_in > per_cta_kb + 1) s_in = per_cta_kb + 1 < 2 ? 2 : per_cta_kb + 1;
                         const int bn_eff = bn < 128 ? bn : 128;

@@ -169,12 +169,14 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
-    // carve-up: [A stages][B stages][input stages (+ dw parameter block each)][epilogue staging][pw BN vectors][barriers]
+    // carve-up: [A stages][B stages][epilogue staging][input stages (+ dw parameter block each)][pw BN vectors][barriers].  A stages and
+    // staging tiles are 16 KB, B stages multiples of 2 KB: everything that needs 1 KB alignment (SWIZZLE_128B atoms) sits in front of the
+    // 128-byte-granular input stages, so the aligned base is the only alignment slack the plan has to budget
     const uint32_t a_off = 0;
     const uint32_t b_off = a_off + p.s_a * TC_A_STAGE_BYTES;
-    const uint32_t in_off = b_off + p.s_b * p.b_stage_bytes;
-    const uint32_t stg_off = (in_off + p.s_in * p.in_stage_stride + 1023u) & ~1023u;   // epilogue staging: [128 px][64 ch] 16-bit, SW128 atoms
-    const uint32_t pw_off = stg_off + (uint32_t)p.n_stg * 16384u;
+    const uint32_t stg_off = b_off + p.s_b * p.b_stage_bytes;                          // epilogue staging: [128 px][64 ch] 16-bit, SW128 atoms
+    const uint32_t in_off = stg_off + (uint32_t)p.n_stg * 16384u;
+    const uint32_t pw_off = in_off + p.s_in * p.in_stage_stride;
     const uint32_t bar_off = pw_off + (p.head ? 3u : 2u) * (uint32_t)p.cpad_all * 4u;     // (head: 16-bit weights use half of their slot)
     TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem + bar_off);
     float2* s_pw_affine = reinterpret_cast<float2*>(smem + pw_off);           // (scale, scale, bias, bias) per output-channel pair
@@ -444,7 +446,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
 #pragma unroll
                     for (int i = 0; i < KS * KS; ++i) wv[i] = *reinterpret_cast<const uint32_t*>(prm + i * 128 + lane * 4);
                 }
-#pragma unroll 1
+#pragma unroll 1                           // (interleaving a team warp's two blocks, tried for the half-K path: conv1 55.4 -> 60.8 us)
                 for (int blk = 0; blk < nblk; ++blk) {
                 const int bidx = member * nblk + blk;                      // 4x4-pixel block of the tile
                 const int ni = bidx / BPI, rem = bidx % BPI, br = rem / BPR, bc = rem % BPR;
