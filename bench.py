@@ -8,7 +8,9 @@ One "step" = one pass of the hot path over one batch of synthetic input: batch 6
 224x224, fp16, MobileNet-NNConv5(dw)+skipadd (BASELINE.json metric config; weak scaling: every
 rank keeps 64 images).  Prints ONE JSON line on rank 0.
 
-  value      whole-job images/s with inputs resident in HBM (CUDA events, max over ranks)
+  value      whole-job images/s with inputs resident in HBM (CUDA events, max over ranks); `--lanes` (default 3) independent
+             forwards are in flight (plan copies with their own activation buffers on their own streams: another batch's kernels fill
+             the idle SM time at every kernel boundary); `single_stream` in the line is the strict one-at-a-time replay
   e2e        same metric through the C-ABI host-buffer call fd_forward_host: pinned-host -> device
              copy of the batch and device -> host copy of the depth maps inside the timed region
   roofline   the dominant kernel's achieved HBM GB/s = algorithmic bytes / launch duration
@@ -60,6 +62,8 @@ def parse():
     ap.add_argument('--no-lib-baseline', action='store_true', help='skip the cuDNN-eager leg')
     ap.add_argument('--no-eval', action='store_true', help='skip the bf16 sharded-evaluation leg (config 4)')
     ap.add_argument('--e2e-steps', type=int, default=200)
+    ap.add_argument('--lanes', type=int, default=3, help='batches in flight: independent plan copies on their own streams '
+                                                         '(fastdepth_b200.engine.ForwardLanes); 1 = strict single stream')
     return ap.parse_args()
 
 
@@ -367,10 +371,14 @@ def main():
     model = models.MobileNetSkipAdd((h, w), pretrained=False, widths=widths)
     model.load_state_dict(sd)
     model = model.eval().to(dev).to(dtype)
-    eng = SkipAddEngine(model)
-    for k, v in (('path', args.path), ('fold_head', args.fold_head), ('graph', args.graph)):
+    from fastdepth_b200.engine import ForwardLanes
+    opts = {'path': args.path, 'fold_head': args.fold_head, 'graph': args.graph}
+    eng = SkipAddEngine(model)                      # the module's own (single-stream) engine: parity check, eval leg, per-kernel table
+    for k, v in opts.items():
         eng.set_option(k, v)
     model.__dict__['_fd_engine'] = eng
+    R = max(1, args.lanes)
+    lanes = ForwardLanes(model, lanes=R, options=opts)
 
     # 4 rotating input batches (different images per rank); a step moves >1 GB through HBM, far more
     # than the 126 MB L2, so nothing of the previous step's input survives in cache.
@@ -380,20 +388,29 @@ def main():
     plan = eng.plan_for(xs[0])
     stream = torch.cuda.current_stream(dev)
     sp = stream.cuda_stream
+    lane_plans = lanes.plans_for(xs[0])
+    lane_streams = lanes.streams_for(dev)
+    lane_y = [torch.empty((n, 1, h, w), dtype=dtype, device=dev) for _ in range(R)]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, fan=None):
+        """CUDA-event time of `steps` calls of fn.  `fan`: the lane streams the calls are spread over -- they all wait for the
+        start event and the end event (on the main stream) waits for all of them."""
         for i in range(warmup):
             fn(i)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        for s_ in (fan or ()):
+            s_.wait_event(e0)
         for i in range(steps):
             fn(i)
+        for s_ in (fan or ()):
+            stream.wait_stream(s_)
         e1.record(stream)
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -405,23 +422,35 @@ def main():
     if sampler:
         sampler.start()
     # ---- value: device-resident inputs ---------------------------------------------------------
-    ms_total = timed(lambda i: plan.forward(xs[i % n_rot], y, sp), args.steps, max(3, args.warmup))
+    # `lanes` forwards in flight: step i runs on lane i % R (own plan copy, own stream); R = 1 is the strict single-stream replay
+    ms_single = timed(lambda i: plan.forward(xs[i % n_rot], y, sp), args.steps, max(3, args.warmup))
+    if R > 1:
+        ms_total = timed(lambda i: lane_plans[i % R].forward(xs[i % n_rot], lane_y[i % R], lane_streams[i % R].cuda_stream),
+                         args.steps, max(3, args.warmup) * R, fan=lane_streams)
+    else:
+        ms_total = ms_single
     # ---- e2e: pinned host buffers through the C-ABI pipeline (fd_pipeline_submit / fd_pipeline_wait): every step
     # uploads its batch from pinned host memory and downloads its depth maps; up to 3 batches are in flight so
     # the PCIe copies overlap the forward of the neighbouring steps.  Timed on the host clock between device-wide
     # synchronisations (the work spans three streams), max over ranks.
     xh = [x.cpu().pin_memory() for x in xs[:3]]
     yh = [torch.empty((n, 1, h, w), dtype=dtype).pin_memory() for _ in range(3)]
+    xh_l = [xh for _ in range(R)]                                    # pinned inputs are read-only: shared by the lanes
+    yh_l = [[torch.empty((n, 1, h, w), dtype=dtype).pin_memory() for _ in range(3)] for _ in range(R)]
     e2e_steps = max(6, args.steps, args.e2e_steps)      # ~0.13 s per repeat at batch 64: long enough to be stable
 
     def run_pipeline(k):
-        tickets = []
+        # every lane has its own fd_pipeline (three batches in flight each: copies of one batch overlap the forward of its
+        # neighbours); batches go round-robin over the lanes, the host waits for a batch 2 * R submissions later
+        pending = []
         for i in range(k):
-            tickets.append(plan.pipeline_submit(xh[i % 3], yh[i % 3]))
-            if i >= 2:
-                plan.pipeline_wait(tickets[i - 2])
-        for t in tickets[-2:]:
-            plan.pipeline_wait(t)
+            lane = i % R
+            pending.append((lane_plans[lane], lane_plans[lane].pipeline_submit(xh_l[lane][(i // R) % 3], yh_l[lane][(i // R) % 3])))
+            if len(pending) > 2 * R:
+                p_, t_ = pending.pop(0)
+                p_.pipeline_wait(t_)
+        for p_, t_ in pending:
+            p_.pipeline_wait(t_)
 
     run_pipeline(8)
     reps = []
@@ -514,13 +543,18 @@ def main():
                                % (args.widths, n, h, w, args.dtype),
                    'global_batch': n * world, 'parallelism': 'image-sharded x%d (no data-path collective)' % world,
                    'path': args.path, 'fold_head': args.fold_head, 'graph': args.graph,
+                   'in_flight': R, 'in_flight_note': '%d independent forwards in flight (plan copies with their own activation buffers on their '
+                                                     'own streams, fastdepth_b200.engine.ForwardLanes): every step is a '
+                                                     'complete forward of its own batch; the strict single-stream replay is `single_stream`' % R,
                    'l2': '4 rotating input batches; one step streams %.2f GB through HBM (>> 126 MB L2)' % (alg_total / 1e9),
                    'weights': 'random-init (synthetic recipe seed 1)'},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': xh[0].numel() * xh[0].element_size(),
                 'd2h_bytes_per_step': yh[0].numel() * yh[0].element_size(), 'ms_per_step': ms_e2e / e2e_steps,
-                'api': 'fd_pipeline_submit/fd_pipeline_wait (C-ABI, pinned host buffers, 3 batches in flight)',
+                'api': 'fd_pipeline_submit/fd_pipeline_wait (C-ABI, pinned host buffers, 3 batches in flight per lane, %d lane(s))' % R,
                 'steps': e2e_steps, 'repeats_ms': [round(r, 3) for r in reps], 'statistic': 'median of 3 repeats, max over ranks each',
                 'sync_call_ms_per_step': ms_sync, 'sync_call_api': 'fd_forward_host'},
+        'single_stream': {'value': world * n * args.steps / (ms_single * 1e-3), 'unit': UNIT, 'ms_per_step': ms_single / args.steps,
+                          'note': 'one forward at a time on one stream (CUDA-graph replay): the latency of a batch'},
         'gpu_launches': plan.launches_per_forward() * args.steps,
         'launches_per_step': plan.launches_per_forward(),
         'clocks': clocks,

@@ -103,7 +103,7 @@ struct fd_plan {
     std::vector<Stage> stages;
     std::vector<Step> steps;
     bool steps_valid = false;
-    int opt_path = 1, opt_fold_head = 1, opt_graph = 1, opt_tma_epilogue = 1, opt_inplace_skip = 1, opt_pdl = 1, opt_wait_sleep_ns = 0;
+    int opt_path = 1, opt_fold_head = 1, opt_graph = 1, opt_tma_epilogue = 1, opt_inplace_skip = 1, opt_pdl = 0, opt_wait_sleep_ns = 0;
     int opt_chain = 1;
     int opt_cluster = 1;
     size_t workspace_bytes = 0;

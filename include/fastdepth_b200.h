@@ -105,7 +105,10 @@ int fd_plan_set_stage_weights(fd_plan* plan, int stage,
  *                (TMA reduce-add); the skip source's stage buffer then holds the decoder output
  *                after fd_forward (set 0 for stage-by-stage inspection)  [default 1]
  *   "pdl"        1 = tensor-core kernels are launched with programmatic dependent launch so that each
- *                kernel's prologue overlaps the previous kernel's tail  [default 1]
+ *                kernel's prologue overlaps the previous kernel's tail.  With one 227 KB CTA per SM the early-launched
+ *                dependents mostly hold SMs idle while they wait for the previous grid: measured 596.8 us per forward
+ *                with it, 589.4 us without (round 2), and it costs more when several plans run concurrently
+ *                [default 0]
  *   "chain"      1 = a run of consecutive 3x3 stride-1 blocks on a small feature map (conv7..conv11 at 14x14) executes as ONE
  *                kernel on 2-CTA clusters with every intermediate activation resident in shared memory; the intermediate
  *                stages' buffers are then not written (set 0 for stage-by-stage inspection)  [default 1]

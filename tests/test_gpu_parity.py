@@ -375,6 +375,29 @@ def test_tile_sharing_clusters_agree_bitwise(widths, monkeypatch):
             assert torch.equal(a, b), (cl, i, kern)
 
 
+def test_forward_lanes_match_the_module_forward():
+    """fastdepth_b200.engine.ForwardLanes (three plan copies on their own streams, batches round-robin) returns, for every batch,
+    the bits the module's own forward returns; the host pipeline of the lanes too."""
+    from fastdepth_b200.engine import ForwardLanes
+    m, _ = make_model(synthetic.STOCK_WIDTHS, torch.float16, (64, 96))
+    xs = [synthetic.synthetic_input(3, 64, 96, seed=40 + i).cuda().half() for i in range(7)]
+    with torch.no_grad():
+        want = [m(x).clone() for x in xs]
+    lanes = ForwardLanes(m, lanes=3)
+    outs = [lanes.forward(x) for x in xs]
+    for (y, done), w in zip(outs, want):
+        done.synchronize()
+        assert torch.equal(y, w)
+    xh = [x.cpu().pin_memory() for x in xs]
+    yh = [torch.empty((3, 1, 64, 96), dtype=torch.float16).pin_memory() for _ in xs]
+    handles = [lanes.submit(a, b, xs[0]) for a, b in zip(xh, yh)]
+    for hnd in handles:
+        lanes.wait(hnd)
+    for b, w in zip(yh, want):
+        assert torch.equal(b, w.cpu())
+    lanes.synchronize()
+
+
 def test_option_validation():
     from fastdepth_b200.engine import SkipAddEngine
     m, _ = make_model(synthetic.STOCK_WIDTHS, torch.float16, (64, 96))
@@ -526,6 +549,7 @@ def test_two_plans_with_different_options_do_not_share_launch_state():
     m, _ = make_model(synthetic.STOCK_WIDTHS, torch.float16, (64, 96))
     x = synthetic.synthetic_input(2, 64, 96, seed=2).cuda().half()
     e1, e2 = SkipAddEngine(m), SkipAddEngine(m)
+    e1.set_option('pdl', 1)
     e2.set_option('pdl', 0)
     e2.set_option('wait_sleep_ns', 300)
     outs = []
