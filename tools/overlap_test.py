@@ -11,7 +11,7 @@ pdl = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 sd = synthetic.synthetic_state_dict(synthetic.STOCK_WIDTHS)
 m = models.MobileNetSkipAdd((224, 224), pretrained=False); m.load_state_dict(sd); m = m.eval().cuda().half()
 xs = [synthetic.synthetic_input(64, 224, 224, seed=i).cuda().half() for i in range(4)]
-for R in (1, 2, 3):
+for R in ((1, 2, 3, 4, 6) if len(sys.argv) > 2 else (1, 2, 3)):
     engs, plans, streams, ys = [], [], [], []
     for r in range(R):
         e = SkipAddEngine(m); e.set_option('pdl', pdl)
