@@ -4,7 +4,7 @@
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 timeout 600 python bench.py > gpurun_out/g_bench.json 2> gpurun_out/g_bench.err
-B="python bench.py --steps 2 --warmup 3 --graph 0 --no-cpu-baseline --no-lib-baseline --no-eval --stage-iters 1 --e2e-steps 6"
+B="python bench.py --lanes 1 --steps 2 --warmup 3 --graph 0 --no-cpu-baseline --no-lib-baseline --no-eval --stage-iters 1 --e2e-steps 6"   # one lane: the 15 launches of a forward in order
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"chain_tc|block_tc|stem_tc" --launch-skip 30 --launch-count 30 --csv --log-file gpurun_out/g_launches.csv $B > gpurun_out/g_ncu_launch.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"chain_tc|block_tc|stem_tc" --launch-skip 30 --launch-count 15 -o gpurun_out/prof_r2g $B > gpurun_out/g_ncu_full.log 2>&1
 timeout 200 python tools/trace_chain.py > gpurun_out/g_trace_chain.txt 2>&1
