@@ -114,6 +114,9 @@ struct fd_plan {
     unsigned long long pipe_next = 0;    // next ticket
     void* stage_x = nullptr;             // device staging for fd_forward_host
     void* stage_y = nullptr;
+    cudaEvent_t last_done = nullptr;     // recorded after every fd_forward on its stream (cross-stream ordering of one plan's buffers)
+    cudaStream_t last_stream = nullptr;
+    bool last_stream_set = false;
     void* l2_flush = nullptr;
     size_t l2_flush_bytes = 0;
     // CUDA graph cache keyed on the (x, y) pointer pair: callers that rotate a few buffers (or let a
@@ -546,12 +549,31 @@ static int ensure_steps(fd_plan* p) {
     return build_steps(p);
 }
 
+static int forward_enqueue(fd_plan* p, const void* x_dev, void* y_dev, cudaStream_t st);
+
 int fd_forward(fd_plan* p, const void* x_dev, void* y_dev, void* stream) {
     if (!p || !x_dev || !y_dev) return fail(FD_ERR_INVALID, "NULL argument");
     DeviceGuard guard(p->device);
     int rc = ensure_steps(p);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    // A plan owns ONE set of activation buffers: a forward enqueued on another stream than the previous one first waits for that
+    // one to finish (stream-ordered, no host synchronisation) instead of silently running into its intermediates.  Concurrency
+    // is spelled with several plans (fastdepth_b200.engine.ForwardLanes).
+    if (!p->last_done) FD_CUDA_OK(cudaEventCreateWithFlags(&p->last_done, cudaEventDisableTiming));
+    if (p->last_stream_set && p->last_stream != st) FD_CUDA_OK(cudaStreamWaitEvent(st, p->last_done, 0));
+    rc = forward_enqueue(p, x_dev, y_dev, st);
+    if (rc) return rc;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone) {
+        FD_CUDA_OK(cudaEventRecord(p->last_done, st));
+        p->last_stream = st; p->last_stream_set = true;
+    }
+    return FD_OK;
+}
+
+static int forward_enqueue(fd_plan* p, const void* x_dev, void* y_dev, cudaStream_t st) {
+    int rc = FD_OK;
     if (!p->opt_graph) return run_steps(p, x_dev, y_dev, st);
 
     // Replay from a CUDA graph captured for this (x, y) pair.
@@ -835,6 +857,7 @@ void fd_plan_destroy(fd_plan* p) {
         if (sl.done) cudaEventDestroy(sl.done);
         if (sl.down) cudaEventDestroy(sl.down);
     }
+    if (p->last_done) cudaEventDestroy(p->last_done);
     if (p->pipe_h2d) cudaStreamDestroy(p->pipe_h2d);
     if (p->pipe_run) cudaStreamDestroy(p->pipe_run);
     if (p->pipe_d2h) cudaStreamDestroy(p->pipe_d2h);

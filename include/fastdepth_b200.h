@@ -124,7 +124,9 @@ int fd_plan_set_option(fd_plan* plan, const char* name, int value);
 int fd_plan_get_option(fd_plan* plan, const char* name, int* value);
 
 /* The hot path.  x_dev: [N,3,H,W] contiguous, plan dtype.  y_dev: [N,1,H,W] contiguous,
- * plan dtype.  Enqueues on `stream`; returns without synchronising.
+ * plan dtype.  Enqueues on `stream`; returns without synchronising.  A plan owns one set of activation
+ * buffers: calls on different streams are ordered after each other by an event (never corrupted, never
+ * overlapped); to keep several forwards in flight use several plans (one per stream).
  * Replaces: pred = model(input)  (reference main.py:74-75 -> models.py:706-732). */
 int fd_forward(fd_plan* plan, const void* x_dev, void* y_dev, void* stream);
 

@@ -398,6 +398,27 @@ def test_forward_lanes_match_the_module_forward():
     lanes.synchronize()
 
 
+def test_one_plan_on_two_streams_is_ordered_not_corrupted():
+    """a plan owns one set of activation buffers.  Forwards enqueued on two different streams without any
+    synchronisation in between must come out as if they had run one after the other."""
+    from fastdepth_b200.engine import SkipAddEngine
+    m, _ = make_model(synthetic.STOCK_WIDTHS, torch.float16, (224, 224))
+    xs = [synthetic.synthetic_input(16, 224, 224, seed=70 + i).cuda().half() for i in range(4)]
+    with torch.no_grad():
+        want = [m(x).clone() for x in xs]
+    torch.cuda.synchronize()
+    eng = SkipAddEngine(m)
+    plan = eng.plan_for(xs[0])
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    ys = [torch.empty_like(w) for w in want]
+    for rep in range(3):
+        for i, x in enumerate(xs):
+            plan.forward(x, ys[i], (s1 if i % 2 == 0 else s2).cuda_stream)
+    torch.cuda.synchronize()
+    for y, w in zip(ys, want):
+        assert torch.equal(y, w)
+
+
 def test_option_validation():
     from fastdepth_b200.engine import SkipAddEngine
     m, _ = make_model(synthetic.STOCK_WIDTHS, torch.float16, (64, 96))
