@@ -134,3 +134,18 @@ def test_skipconcat_surface():
     descs, _, _ = plan.describe(m.eval())
     assert [(d['skip_src'], d.get('skip_mode', 0)) for d in descs[14:19]] == [(-1, 0), (5, 1), (3, 1), (1, 1), (-1, 0)]
     assert [d['c_in'] for d in descs[14:20]] == [1024, 512, 512, 256, 128, 32]
+
+
+def test_forward_lanes_surface_without_gpu():
+    """fastdepth_b200.engine.ForwardLanes is plain host bookkeeping until a batch arrives: it can be built anywhere, refuses
+    nonsense, and -- like the module -- has no CPU fallback."""
+    from fastdepth_b200.engine import ForwardLanes
+    m = models.MobileNetSkipAdd((64, 96), pretrained=False).eval()
+    lanes = ForwardLanes(m, lanes=3)
+    assert len(lanes) == 3 and all(e.options.get('pdl') == 0 for e in lanes.engines)      # PDL stays off on concurrent lanes
+    assert ForwardLanes(m, lanes=1).engines[0].options == {}
+    with pytest.raises(ValueError):
+        ForwardLanes(m, lanes=0)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            lanes.engines[0].plan_for(torch.rand(1, 3, 64, 96))
