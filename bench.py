@@ -251,7 +251,7 @@ def cpu_forward_rate(sd, h, w, budget_s, min_steps, warmup, batch=None):
     return batch / per, batch, len(times), per
 
 
-def run_eval(rank, world, dev, widths, sd, h, w, n):
+def run_eval(rank, world, dev, widths, sd, h, w, n, lanes=1):
     """BASELINE config 4's shape on however many ranks there are: bf16, n images per rank, image-sharded, per-image
     metrics on device, ONE all-reduce(SUM) of 11 doubles (reference metrics.py:71-95, main.py:80-82).  Returns rank 0's
     report.  Outside every timed region of the headline metric; the oracle is used here as the checker only (targets
@@ -272,7 +272,7 @@ def run_eval(rank, world, dev, widths, sd, h, w, n):
     tgt = synthetic.synthetic_target(ref, seed=6000 + rank)
     xd, td = x.to(dev).to(dt), tgt.to(dev)
     # (a) the sharded evaluation through the product's own entry point (forward + device metrics + the one collective)
-    ours, sums = evaluate.evaluate(m, [(xd[:n // 2], td[:n // 2]), (xd[n // 2:], td[n // 2:])], dev, return_sums=True)
+    ours, sums = evaluate.evaluate(m, [(xd[:n // 2], td[:n // 2]), (xd[n // 2:], td[n // 2:])], dev, return_sums=True, lanes=min(2, lanes))
     # (b) the collective alone, timed on the device: 11 doubles, latency only
     ar_us = None
     if world > 1:
@@ -474,7 +474,7 @@ def main():
     # ---- config-4 evaluation leg: every rank takes part (forward in bf16, device metrics, the path's one collective)
     eval_info = None
     if not args.no_eval and (h, w) == (224, 224):
-        eval_info = run_eval(rank, world, dev, widths, sd, h, w, n)
+        eval_info = run_eval(rank, world, dev, widths, sd, h, w, n, lanes=R)
 
     if rank != 0:
         if world > 1:

@@ -41,17 +41,39 @@ def finalize(sums):
 
 
 @torch.no_grad()
-def evaluate(model, batches, device, group=None, return_sums=False):
+def evaluate(model, batches, device, group=None, return_sums=False, lanes=1):
     """``batches`` yields (input [b,3,H,W], target [b,1,H,W]) for THIS rank's shard (host or
     device tensors).  Returns the averaged metrics over all ranks' images (with ``return_sums`` also the reduced
-    11-double sum vector, for bookkeeping checks)."""
-    sums = new_sums(device)
+    11-double sum vector, for bookkeeping checks).
+
+    ``lanes`` > 1 keeps that many batches in flight (``engine.ForwardLanes``: plan copies on their own streams; each lane
+    accumulates into its own sum vector on its own stream, the vectors are added at the end).  The result does not depend on
+    it: every per-image metric enters the fp64 sums as an fp32-rounded value, so the additions are exact in any order."""
     model.eval()
     dtype = next(model.parameters()).dtype
-    for inp, tgt in batches:
-        inp = inp.to(device=device, dtype=dtype, non_blocking=True)
-        tgt = tgt.to(device=device, dtype=torch.float32, non_blocking=True)
-        pred = model(inp)
-        metrics_accumulate(pred, tgt, sums)
+    if lanes > 1:
+        from .engine import ForwardLanes
+        fl = ForwardLanes(model, lanes=lanes)
+        lane_sums = [new_sums(device) for _ in range(lanes)]
+        streams = fl.streams_for(torch.device(device))
+        for inp, tgt in batches:
+            inp = inp.to(device=device, dtype=dtype, non_blocking=True)
+            tgt = tgt.to(device=device, dtype=torch.float32, non_blocking=True)
+            lane = fl.next
+            pred, _ = fl.forward(inp)                       # the lane's stream first waits for the current stream (inp, tgt ready)
+            tgt.record_stream(streams[lane])
+            with torch.cuda.stream(streams[lane]):
+                metrics_accumulate(pred, tgt, lane_sums[lane])
+        fl.synchronize()
+        sums = lane_sums[0]
+        for other in lane_sums[1:]:
+            sums = sums + other
+    else:
+        sums = new_sums(device)
+        for inp, tgt in batches:
+            inp = inp.to(device=device, dtype=dtype, non_blocking=True)
+            tgt = tgt.to(device=device, dtype=torch.float32, non_blocking=True)
+            pred = model(inp)
+            metrics_accumulate(pred, tgt, sums)
     reduce_sums(sums, group)
     return (finalize(sums), sums) if return_sums else finalize(sums)

@@ -215,6 +215,11 @@ def test_sharded_evaluate_single_gpu():
     assert got['count'] == n
     for k in ('rmse', 'mae', 'delta1', 'absrel', 'lg10'):
         assert got[k] == pytest.approx(want[k], rel=2e-3, abs=1e-4), k
+    # several batches in flight (three plan copies on their own streams, one sum vector per lane): the same sums, bit for bit
+    batches = [(x[i:i + 1], tgt[i:i + 1]) for i in range(6)]
+    _, s1 = evaluate.evaluate(m, batches, torch.device('cuda:0'), return_sums=True)
+    _, s3 = evaluate.evaluate(m, batches, torch.device('cuda:0'), return_sums=True, lanes=3)
+    assert torch.equal(s1, s3)
 
 
 def test_pipeline_api_matches_forward():
