@@ -101,7 +101,6 @@ struct TcParams {
     const void* dwp;      // [kblocks] x { [k*k][64] 16-bit taps, [64] fp32 scale, [64] fp32 bias }
     const float2* pw_affine;  // [cpad_all / 2] x (scale, scale, bias, bias) of a channel pair
     const float* head_w;  // [cpad_all]
-    int cl_debug;         // bring-up: bit 0 = commit a_empty locally only (no multicast; flow control of the A ring is then unsafe)
     int dw_teams;         // 2: the depthwise warps form two teams of four that take alternate K-block steps, two 4x4 blocks per warp
                           // (needs even s_in and s_a); 1: eight warps in lock-step, one block each
     int epi_high;         // 1: the epilogue runs on warps 8..15 and the depthwise on 0..7 (default: the other way round).  Which role
@@ -209,7 +208,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         for (int i = 0; i < TC_MAX_IN; ++i) { mbar_init(smem_u32(&bars->in_full[i]), 1); mbar_init(smem_u32(&bars->in_empty[i]), dw_arrivals); }
         // cluster mode: an A stage is full after ONE arrival (the owner's broadcast thread, or this CTA's own expect_tx for a
         // tile that arrives by bulk copy) and free again when the MMA streams of all cs CTAs have committed past it
-        for (int i = 0; i < TC_MAX_A; ++i) { mbar_init(smem_u32(&bars->a_full[i]), CL ? 1u : dw_arrivals); mbar_init(smem_u32(&bars->a_empty[i]), (CL && (p.cl_debug & 1)) ? 1u : cs); }
+        for (int i = 0; i < TC_MAX_A; ++i) { mbar_init(smem_u32(&bars->a_full[i]), CL ? 1u : dw_arrivals); mbar_init(smem_u32(&bars->a_empty[i]), cs); }
         for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars->dw_done[i]), TC_DW_WARPS);
         for (int i = 0; i < TC_MAX_B; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), wmc); }   // multicast: freed by all
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), (p.epi_colsplit || p.epi_wide) ? TC_EPI_WARPS : TC_EPI_WARPS / 2); }
@@ -369,7 +368,7 @@ block_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                             else umma_commit(bar_b_empty + 8u * sb);
                         }
                     }
-                    if (CL && !(p.cl_debug & 1)) umma_commit_multicast(bar_a_empty + 8u * ra.s, cl_mask);    // frees the stage in every CTA's count
+                    if constexpr (CL) umma_commit_multicast(bar_a_empty + 8u * ra.s, cl_mask);    // frees the stage in every CTA's count
                     else umma_commit(bar_a_empty + 8u * ra.s);
                     TC_TRACE(5, tr); ++tr;
                 }
@@ -1068,7 +1067,6 @@ int block_tc_prepare(int dtype, const BlockArgs& a, const float* head_w, float h
         while (want > 1 && !(p.cs == 1 && !p.b_resident && n_tiles % want == 0 && p.bn % (8 * want) == 0 && n_tiles / want >= 1)) want >>= 1;
         p.wmc = want < 1 ? 1 : want;
     }
-    { const char* e = getenv("FD_TC_CL_DEBUG"); p.cl_debug = e ? atoi(e) : 0; }        // bring-up switches of the cluster mode
     bp->smem_bytes = (size_t)po.smem_bytes;
     const int taps = g.ksize * g.ksize;
     (void)splits;
